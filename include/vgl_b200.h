@@ -1,0 +1,205 @@
+/*
+ * vgl_b200.h — C ABI of libvgl_b200.so: the B200-native (sm_100a) backend for VectorGraphLibrary's
+ * frontier-processing hot path (GraphAbstractions scatter/gather/compute/reduce/generate_new_frontier over
+ * VectCSRGraph / VerticesArray / EdgesArray / frontier, and BFS / PageRank / SSSP / CC built on them).
+ *
+ * The reference has no FFI for this path: the backend is a compile-time plugin slot
+ * (architecture_independent_api.h:33-43, `#define VGL_GRAPH_ABSTRACTIONS <BackendClass>`), so "what the reference's
+ * FFI would bind" is the set of calls its GPU backend class makes (vgl_compute_api/gpu/graph_abstractions_gpu.h:16-190)
+ * plus the data-structure moves around it. Each entry point below cites the reference interface it replaces.
+ * Device lambdas cannot cross a C ABI; the arbitrary-lambda path is the header-only template shim
+ * include/vgl_b200/graph_abstractions_b200.cuh, which sits on top of these entry points.
+ *
+ * Conventions: every function returns 0 on success or a VGLB_E* code; the message is in vglb_last_error()
+ * (reference: `throw "literal"` / SAFE_CALL, vgl_runtime/helpers/gpu_API/cuda_error_handling.h:7-27).
+ * There is NO CPU fallback: every compute entry point fails with VGLB_ENODEVICE when no CUDA device is usable.
+ * Pointers named d_* are device pointers owned by the caller (vglb_malloc) unless stated; h_* are host pointers
+ * borrowed for the duration of the call. Vertex ids are int32, row pointers / edge positions int64, levels / labels
+ * int32, ranks / distances / weights fp32.
+ */
+#ifndef VGL_B200_H
+#define VGL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VGLB_OK 0
+#define VGLB_EINVAL 1      /* bad argument (reference: throw "Error in ... wrong ...", common/advance.hpp:19-26) */
+#define VGLB_ENODEVICE 2   /* no usable CUDA device: there is no CPU fallback */
+#define VGLB_ECUDA 3       /* CUDA runtime / kernel failure (SAFE_CALL / SAFE_KERNEL_CALL) */
+#define VGLB_ENOMEM 4
+#define VGLB_ENCCL 5
+#define VGLB_EUNSORTED 6   /* CSR rows are not degree-sorted descending (not a VectCSR layout) */
+
+/* TraversalDirection, framework_types.h:115-119 */
+#define VGLB_SCATTER 0
+#define VGLB_GATHER 1
+#define VGLB_ORIGINAL 2
+
+/* BFS constants, algorithms/bfs/change_state/change_state.h:21-23 */
+#define VGLB_UNVISITED_VERTEX (-1)
+#define VGLB_FIRST_LEVEL_VERTEX 1
+
+typedef struct vglb_ctx vglb_ctx;
+typedef struct vglb_graph vglb_graph;
+
+/* ---- runtime: VGL_RUNTIME::init_library -> select_device (vgl_runtime.hpp:5-16, gpu_API/select_device.cuh:5-8) ---- */
+int vglb_init(int device, vglb_ctx **out_ctx);
+int vglb_finalize(vglb_ctx *ctx);
+const char *vglb_last_error(void);
+int vglb_device_count(void);
+int vglb_synchronize(vglb_ctx *ctx);
+/* the CUDA stream every kernel of this context is launched on (a cudaStream_t), for event timing by the caller */
+void *vglb_stream(vglb_ctx *ctx);
+
+/* ---- memory: MemoryAPI::allocate_array / free_array / move_array_to_device (memory_API.hpp:3-15,95-101); explicit
+ *      HBM allocations instead of cudaMallocManaged ---- */
+int vglb_malloc(vglb_ctx *ctx, size_t bytes, void **d_ptr);
+int vglb_free(vglb_ctx *ctx, void *d_ptr);
+int vglb_memcpy_h2d(vglb_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
+int vglb_memcpy_d2h(vglb_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+int vglb_memset(vglb_ctx *ctx, void *d_dst, int byte_value, size_t bytes);
+int vglb_host_alloc_pinned(size_t bytes, void **h_ptr);
+int vglb_host_free_pinned(void *h_ptr);
+/* write `bytes` of a private scratch buffer (> L2) so the next timed step starts with a cold L2 */
+int vglb_flush_l2(vglb_ctx *ctx);
+
+/* ---- synthetic inputs (include/vglb_synth.h), device and host twins producing identical edges ---- */
+int vglb_generate_edges_device(vglb_ctx *ctx, int kind, int scale, int64_t edges, uint64_t seed, int a, int b, int c,
+                               int32_t *d_src, int32_t *d_dst);
+int vglb_generate_edges_host(int kind, int scale, int64_t edges, uint64_t seed, int a, int b, int c,
+                             int32_t *h_src, int32_t *h_dst);
+
+/* ---- graph: VGL_Graph::import -> VectorCSRGraph::import (vgl_graph.hpp:57-68, vect_csr/import.hpp:257-337) ----
+ * Builds, ON THE GPU, the reference's degree-sorted CSR: vertices stable-sorted by out-degree descending
+ * (sorter.h:55-92), edges stable-sorted by new src (edges_container.h:101-161) => row order and adjacency order are
+ * bit-identical to VectorCSRGraph's. `d_src/d_dst` are device pointers when src_on_device != 0, else host pointers.
+ * flags: VGLB_GRAPH_WITH_INCOMING also builds the incoming CSR on the SAME (SCATTER) numbering (bottom-up BFS);
+ *        VGLB_GRAPH_WITH_EDGE_ORDER keeps edges_reorder_indexes (CSR position -> input edge index). */
+#define VGLB_GRAPH_WITH_INCOMING 1
+#define VGLB_GRAPH_WITH_EDGE_ORDER 2
+int vglb_graph_from_edges(vglb_ctx *ctx, int32_t vertices, int64_t edges, const int32_t *src, const int32_t *dst,
+                          int src_on_device, int flags, vglb_graph **out_graph);
+/* VGL_Graph::move_to_device (vect_csr_graph.hpp:185-196): borrow an already-built VectorCSRGraph (host arrays in
+ * sorted numbering: get_vertex_pointers()/get_adjacent_ids(), vect_csr_graph.h:99-100) and copy it to HBM.
+ * h_orig_to_sorted (forward_conversion) may be NULL (identity). Incoming arrays may be NULL. */
+int vglb_graph_from_csr(vglb_ctx *ctx, int32_t vertices, int64_t edges, const int64_t *h_out_ptr,
+                        const int32_t *h_out_adj, const int32_t *h_orig_to_sorted, const int64_t *h_in_ptr,
+                        const int32_t *h_in_adj, vglb_graph **out_graph);
+int vglb_graph_free(vglb_ctx *ctx, vglb_graph *g);
+
+#define VGLB_NUM_TIERS 8
+typedef struct vglb_graph_info
+{
+    int32_t vertices;
+    int64_t edges;
+    int32_t has_incoming;
+    int32_t max_degree;
+    /* tier_border[t] = first sorted id whose out-degree is < tier_degree[t]; tiers are contiguous id ranges because
+     * ids are degree-sorted (reference: vector_engine/vector_core_threshold_vertex, vect_csr/nec_api.hpp:5-50) */
+    int32_t tier_degree[VGLB_NUM_TIERS];
+    int32_t tier_border[VGLB_NUM_TIERS];
+    /* device pointers (read-only for callers) */
+    const int64_t *d_out_ptr;
+    const int32_t *d_out_adj;
+    const int64_t *d_in_ptr;
+    const int32_t *d_in_adj;
+    const int32_t *d_orig_to_sorted; /* forward_conversion */
+    const int32_t *d_sorted_to_orig; /* backward_conversion */
+    const int64_t *d_edge_order;     /* edges_reorder_indexes or NULL */
+} vglb_graph_info;
+int vglb_graph_get_info(vglb_graph *g, vglb_graph_info *info);
+/* threshold vertex for an arbitrary degree threshold (estimate_thresholds twin) */
+int vglb_graph_threshold_vertex(vglb_ctx *ctx, vglb_graph *g, int32_t degree_threshold, int32_t *out_vertex);
+
+/* ---- vertices / edges arrays ----
+ * VerticesArray::reorder / VGL_Graph::reorder (vgl_graph/reorder.hpp:3-170, cuda_reorder.cu:5-71): permute a
+ * 4-byte-element vertex array between ORIGINAL and SCATTER numbering (out-of-place gather). */
+int vglb_varray_reorder_u32(vglb_ctx *ctx, vglb_graph *g, const uint32_t *d_in, uint32_t *d_out, int from_dir, int to_dir);
+/* EdgesArray weights for every out-CSR position from vglb_edge_weight(orig_src, orig_dst, seed)
+ * (reference: EdgesArray::set_all_random, vect_csr_edges_array.hpp:49-65) */
+int vglb_earray_fill_synthetic_weights(vglb_ctx *ctx, vglb_graph *g, uint64_t seed, float *d_weights);
+/* per-vertex in-degree without self loops in SCATTER numbering (pr.hpp:28-73) */
+int vglb_graph_indegree_noloops(vglb_ctx *ctx, vglb_graph *g, int32_t *d_indeg);
+
+/* ---- per-run counters: PerformanceStats (performance_stats.h:104, multicore/advance_worker.hpp:305-318) ---- */
+typedef struct vglb_stats
+{
+    double seconds;              /* device time of the algorithm loop (CUDA events on the context stream) */
+    int64_t iterations;          /* BFS levels / PR sweeps / SSSP rounds / CC hook rounds */
+    int64_t edges_inspected;     /* e: edges actually read */
+    int64_t vertices_processed;  /* f: frontier vertices whose row range was read */
+    int64_t frontier_bytes;      /* g: frontier bytes written + read */
+    int64_t algorithmic_bytes;   /* SURVEY §8(d) formula evaluated with the counters above */
+    int64_t kernel_launches;     /* kernels launched by this call */
+    int32_t bottom_up_levels;    /* BFS only */
+    int32_t reserved;
+} vglb_stats;
+
+/* ---- fused algorithms (the four call sites of SURVEY §8 a11-a14) ---- */
+
+/* PageRank, multicore semantics (algorithms/pr/pr.hpp:7-148): r'[u] = k + d*(sum_{u->v, v!=u} r[v]/indeg_noloops(v) + D).
+ * Runs exactly `iters` sweeps; d_ranks (fp32[V]) is returned in SCATTER numbering. */
+int vglb_pagerank(vglb_ctx *ctx, vglb_graph *g, int iters, float damping, float *d_ranks, vglb_stats *stats);
+
+/* BFS levels (algorithms/bfs/bfs.hpp:5-86; DO heuristic change_state.hpp:100-141): source = 1, unreachable = -1,
+ * SCATTER numbering. direction_optimising needs a graph built WITH_INCOMING. alpha/beta <= 0 select 15 / 18. */
+typedef struct vglb_bfs_opts
+{
+    int32_t direction_optimising;
+    int32_t alpha;
+    int32_t beta;
+    int32_t reserved;
+} vglb_bfs_opts;
+int vglb_bfs(vglb_ctx *ctx, vglb_graph *g, int32_t source_sorted, int32_t *d_levels, const vglb_bfs_opts *opts,
+             vglb_stats *stats);
+
+/* SSSP, frontier Bellman-Ford (algorithms/sssp/shortest_paths.hpp:7-78, gpu_shortest_paths.hpp:133-196): min-plus
+ * fixed point in fp32, unreachable = FLT_MAX; d_weights indexed by out-CSR position. */
+int vglb_sssp(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, int32_t source_sorted, float *d_dist,
+              vglb_stats *stats);
+
+/* CC, min-label hook + pointer jumping (algorithms/cc/shiloach_vishkin.hpp:7-88): labels[v] = min SCATTER id over
+ * {v} U ancestors(v) (= component minimum on symmetric graphs). */
+int vglb_cc(vglb_ctx *ctx, vglb_graph *g, int32_t *d_labels, vglb_stats *stats);
+
+/* ---- operators with fixed predicates (generate_new_frontier / reduce / compute without lambdas) ----
+ * FrontierVectorCSR (frontier_vect_csr.h:5-53): sparse id queue + dense bitmap, chosen by density. */
+typedef struct vglb_frontier vglb_frontier;
+#define VGLB_FRONTIER_ALL_ACTIVE 0
+#define VGLB_FRONTIER_DENSE 1
+#define VGLB_FRONTIER_SPARSE 2
+int vglb_frontier_create(vglb_ctx *ctx, vglb_graph *g, vglb_frontier **out);
+int vglb_frontier_destroy(vglb_ctx *ctx, vglb_frontier *f);
+int vglb_frontier_set_all_active(vglb_ctx *ctx, vglb_frontier *f);
+int vglb_frontier_clear(vglb_ctx *ctx, vglb_frontier *f);
+int vglb_frontier_add_vertex(vglb_ctx *ctx, vglb_frontier *f, int32_t v);
+typedef struct vglb_frontier_info
+{
+    int32_t sparsity_type;
+    int32_t size;                /* number of active vertices */
+    int64_t neighbours;          /* sum of their degrees */
+    int32_t tier_size[3];        /* active vertices per tier (large / medium / small) */
+    int32_t reserved;
+    const int32_t *d_ids;        /* ascending ids when SPARSE */
+    const uint32_t *d_bitmap;    /* V/32 words, always valid */
+} vglb_frontier_info;
+int vglb_frontier_get_info(vglb_ctx *ctx, vglb_frontier *f, vglb_frontier_info *info);
+/* generate_new_frontier (common/generate_new_frontier.hpp:4-43) with the predicates the four algorithms use:
+ * flags given explicitly, `values[v] == key` (BFS on_next_level), `a[v] != b[v]` (SSSP changes_occurred). */
+int vglb_gnf_from_flags(vglb_ctx *ctx, vglb_frontier *f, const int32_t *d_flags);
+int vglb_gnf_eq_i32(vglb_ctx *ctx, vglb_frontier *f, const int32_t *d_values, int32_t key);
+int vglb_gnf_ne_u32(vglb_ctx *ctx, vglb_frontier *f, const uint32_t *d_a, const uint32_t *d_b);
+/* reduce (common/reduce.hpp:4-67): sum / max of a vertex array over the frontier */
+int vglb_reduce_sum_i32(vglb_ctx *ctx, vglb_frontier *f, const int32_t *d_values, int64_t *out);
+int vglb_reduce_sum_f32(vglb_ctx *ctx, vglb_frontier *f, const float *d_values, double *out);
+int vglb_reduce_max_i32(vglb_ctx *ctx, vglb_frontier *f, const int32_t *d_values, int32_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VGL_B200_H */

@@ -1,0 +1,180 @@
+// common.cuh — internal declarations shared by the libvgl_b200 translation units (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "vgl_b200.h"
+#include "vglb_synth.h"
+
+#define VGLB_SM_COUNT_B200 148
+
+void vglb_set_error(const char *fmt, ...);
+
+// SAFE_CALL twin (cuda_error_handling.h:7-13): record the message and return an error code instead of throwing.
+#define CUDA_TRY(call)                                                                               \
+    do                                                                                               \
+    {                                                                                                \
+        cudaError_t err__ = (call);                                                                  \
+        if (err__ != cudaSuccess)                                                                    \
+        {                                                                                            \
+            vglb_set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(err__), __FILE__,       \
+                           __LINE__, #call);                                                         \
+            return VGLB_ECUDA;                                                                       \
+        }                                                                                            \
+    } while (0)
+
+#define KERNEL_TRY() CUDA_TRY(cudaGetLastError())
+
+#define VGLB_REQUIRE(cond, msg)                                       \
+    do                                                                \
+    {                                                                 \
+        if (!(cond))                                                  \
+        {                                                             \
+            vglb_set_error("%s (%s:%d)", msg, __FILE__, __LINE__);    \
+            return VGLB_EINVAL;                                       \
+        }                                                             \
+    } while (0)
+
+struct vglb_ctx
+{
+    int device;
+    int sm_count;
+    size_t l2_bytes;
+    cudaStream_t stream;
+    cudaEvent_t ev_start, ev_stop;
+    // host-visible scratch for counters read back once per level / round
+    int64_t *h_counters;   // pinned, 64 x int64
+    int64_t *d_counters;   // device, 64 x int64
+    void *d_flush;         // L2 flush buffer
+    size_t flush_bytes;
+    int64_t launches;      // kernels launched since the last reset (gpu_launches evidence)
+};
+
+struct vglb_graph
+{
+    int32_t V;
+    int64_t E;
+    int32_t max_degree;
+    int64_t *d_out_ptr;
+    int32_t *d_out_adj;
+    int64_t *d_in_ptr;
+    int32_t *d_in_adj;
+    int32_t *d_fwd; // orig -> sorted
+    int32_t *d_bwd; // sorted -> orig
+    int64_t *d_edge_order;
+    int32_t tier_degree[VGLB_NUM_TIERS];
+    int32_t tier_border[VGLB_NUM_TIERS];
+    // lazily created per-algorithm state (owned by the graph, freed with it)
+    float *d_pr_inv;       // 1/indeg_noloops (0 when none), SCATTER numbering
+    float *d_pr_contrib[2];
+    double *d_pr_dangling; // one slot per sweep
+    int pr_dangling_slots;
+    // BFS / SSSP / CC scratch
+    uint32_t *d_visited, *d_front_bm[2];
+    int32_t *d_queue[2];
+    int32_t *d_scratch_i32;
+    int bfs_ready;
+};
+
+struct vglb_frontier
+{
+    vglb_graph *g;
+    int32_t sparsity_type;
+    int32_t size;
+    int64_t neighbours;
+    int32_t tier_size[3];
+    int32_t *d_ids;
+    uint32_t *d_bitmap;
+    int32_t *d_block_counts;
+};
+
+// degree thresholds of the tiers: tier t holds rows with degree in [tier_degree[t], tier_degree[t-1]).
+// CTA per row | warp per row | 16 | 8 | 4 | 2 lanes per row | 1 lane per row (degree 1) | degree 0
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+constexpr int32_t vglb_tier_degree(int t)
+{
+    return t == 0 ? 4096 : t == 1 ? 32 : t == 2 ? 16 : t == 3 ? 8 : t == 4 ? 4 : t == 5 ? 2 : t == 6 ? 1 : 0;
+}
+
+int vglb_graph_compute_tiers(vglb_ctx *ctx, vglb_graph *g);
+int vglb_graph_alloc_common(vglb_ctx *ctx, vglb_graph *g);
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+#ifdef __CUDACC__
+// ---- device helpers -------------------------------------------------------------------------------------------
+
+// L2 eviction policies (sm_100a accepts the bare .L2::evict_* qualifier only on 256-bit loads, so 32/128-bit loads
+// carry a createpolicy descriptor through .L2::cache_hint).
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// streaming loads of CSR column indices / weights: read once, keep out of L1 and first to leave L2
+__device__ __forceinline__ int4 ld_stream_v4(const int4 *p, uint64_t pol)
+{
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ int ld_stream_s32(const int *p, uint64_t pol)
+{
+    int r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ float ld_stream_f32(const float *p, uint64_t pol)
+{
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));
+    return r;
+}
+// gathered vertex value: random 4-byte reads of a V-sized vector that should stay L2-resident (L1 allocating)
+__device__ __forceinline__ float ld_gather_f32(const float *p, uint64_t pol)
+{
+    float r;
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ int ld_gather_s32(const int *p, uint64_t pol)
+{
+    int r;
+    asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+    return r;
+}
+
+__device__ __forceinline__ float warp_sum_f32(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_f64(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ long long warp_sum_i64(long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+#endif

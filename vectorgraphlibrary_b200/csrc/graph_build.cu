@@ -1,0 +1,534 @@
+// graph_build.cu — device VectCSR layout: VGL_Graph::import -> VectorCSRGraph::import rebuilt on the GPU.
+//
+// Reference behaviour reproduced bit-for-bit (vgl_datastructures/graphs/undirected_containers/vect_csr/import.hpp:257-337):
+//   extract_connection_count (:5-57)       -> out-degree histogram with atomics
+//   sort_vertices_by_degree (:61-99)       -> STABLE sort of ids by degree descending (sorter.h:55-92 std::stable_sort)
+//                                             == stable LSD radix sort of (~degree) with ascending ids as payload
+//   renumber_vertices (edges_container.h:163-213) + preprocess_into_csr_based (:101-161)
+//                                          -> STABLE sort of edges by new src id, payload = input edge index
+//   construct_CSR (import.hpp:103-153)     -> row pointers = exclusive scan of sorted degrees
+//   estimate_thresholds (nec_api.hpp:5-50) -> tier borders (contiguous id ranges because ids are degree-sorted)
+// The sort/scan primitives are CUB's (toolkit library) — graph construction is setup, outside every timed region
+// (reference: bfs.hpp:76-79 starts its timer after import); the hot path kernels are hand-written (pagerank.cu, ...).
+// B200 layout choices that differ from the reference: the incoming CSR is built on the SAME (SCATTER) numbering as
+// the outgoing one so top-down and bottom-up BFS share one levels array / visited bitmap, and no
+// VectorExtension (ELL copy of the tail) is kept — sub-warp row groups read the CSR tail coalesced instead.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace
+{
+
+__global__ void degree_histogram_kernel(const int32_t *__restrict__ ids, int64_t n, int32_t V, int32_t *__restrict__ deg,
+                                        int *__restrict__ bad)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride)
+    {
+        int32_t v = ids[i];
+        if (v < 0 || v >= V) { *bad = 1; continue; }
+        atomicAdd(&deg[v], 1);
+    }
+}
+
+__global__ void range_check_kernel(const int32_t *__restrict__ ids, int64_t n, int32_t V, int *__restrict__ bad)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride)
+        if (ids[i] < 0 || ids[i] >= V) *bad = 1;
+}
+
+__global__ void degree_sort_keys_kernel(const int32_t *__restrict__ deg, int32_t V, uint32_t *__restrict__ keys,
+                                        uint32_t *__restrict__ ids)
+{
+    int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < V)
+    {
+        keys[v] = ~(uint32_t)deg[v]; // ascending ~deg == descending deg; stable => ascending original id in ties
+        ids[v] = (uint32_t)v;
+    }
+}
+
+__global__ void conversions_kernel(const uint32_t *__restrict__ sorted_ids, const int32_t *__restrict__ deg, int32_t V,
+                                   int32_t *__restrict__ fwd, int32_t *__restrict__ bwd, int64_t *__restrict__ deg_sorted)
+{
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < V)
+    {
+        int32_t orig = (int32_t)sorted_ids[i];
+        bwd[i] = orig;
+        fwd[orig] = i;
+        deg_sorted[i] = deg[orig];
+    }
+    if (i == V) deg_sorted[V] = 0;
+}
+
+__global__ void edge_keys_kernel(const int32_t *__restrict__ key_ids, const int32_t *__restrict__ fwd, int64_t E,
+                                 uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < E; i += stride)
+    {
+        keys[i] = (uint32_t)fwd[key_ids[i]];
+        vals[i] = (uint32_t)i;
+    }
+}
+
+__global__ void gather_adj_kernel(const uint32_t *__restrict__ order, const int32_t *__restrict__ other_ids,
+                                  const int32_t *__restrict__ fwd, int64_t E, int32_t *__restrict__ adj,
+                                  int64_t *__restrict__ edge_order)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; p < E; p += stride)
+    {
+        uint32_t e = order[p];
+        adj[p] = fwd[other_ids[e]];
+        if (edge_order) edge_order[p] = (int64_t)e;
+    }
+}
+
+// in-degree (on the SCATTER numbering) as int64 for the scan
+__global__ void indegree_sorted_kernel(const int32_t *__restrict__ dst, const int32_t *__restrict__ fwd, int64_t E,
+                                       unsigned long long *__restrict__ indeg)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < E; i += stride) atomicAdd(&indeg[fwd[dst[i]]], 1ULL);
+}
+
+__global__ void iota_kernel(int32_t *a, int32_t n)
+{
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = i;
+}
+
+__global__ void invert_perm_kernel(const int32_t *__restrict__ fwd, int32_t *__restrict__ bwd, int32_t n)
+{
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) bwd[fwd[i]] = i;
+}
+
+// tier borders: border[t] = first id whose degree < tier_degree[t]; also checks the rows are degree-sorted.
+__global__ void tier_border_kernel(const int64_t *__restrict__ ptr, int32_t V, int32_t *__restrict__ out /*[NUM_TIERS+2]*/)
+{
+    int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const int64_t p0 = ptr[v], p1 = ptr[v + 1];
+    const int64_t d = p1 - p0;
+    const int64_t dn = (v == V - 1) ? -1 : ptr[v + 2] - p1;
+    if (v == 0) out[VGLB_NUM_TIERS] = (int32_t)(d > 0x7fffffff ? 0x7fffffff : d); // max degree
+    if (dn > d) out[VGLB_NUM_TIERS + 1] = 1;                                       // not sorted
+#pragma unroll
+    for (int t = 0; t < VGLB_NUM_TIERS; t++)
+    {
+        const int64_t T = vglb_tier_degree(t);
+        if (d >= T && dn < T) out[t] = v + 1;
+    }
+}
+
+} // namespace
+
+
+static int bits_for(int32_t V)
+{
+    int b = 1;
+    while (b < 32 && ((int64_t)1 << b) < (int64_t)V) b++;
+    return b;
+}
+
+int vglb_graph_compute_tiers(vglb_ctx *ctx, vglb_graph *g)
+{
+    int32_t *d_out = (int32_t *)ctx->d_counters; // reuse the counter block
+    CUDA_TRY(cudaMemsetAsync(d_out, 0, (VGLB_NUM_TIERS + 2) * sizeof(int32_t), ctx->stream));
+    if (g->V > 0)
+    {
+        tier_border_kernel<<<(unsigned)ceil_div64(g->V, 256), 256, 0, ctx->stream>>>(g->d_out_ptr, g->V, d_out);
+        KERNEL_TRY();
+    }
+    int32_t h[VGLB_NUM_TIERS + 2];
+    CUDA_TRY(cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(d_out, 0, (VGLB_NUM_TIERS + 2) * sizeof(int32_t), ctx->stream));
+    if (h[VGLB_NUM_TIERS + 1])
+    {
+        vglb_set_error("graph rows are not sorted by degree descending: not a VectCSR layout");
+        return VGLB_EUNSORTED;
+    }
+    for (int t = 0; t < VGLB_NUM_TIERS; t++)
+    {
+        g->tier_degree[t] = vglb_tier_degree(t);
+        g->tier_border[t] = h[t];
+    }
+    // borders must be monotone even when a tier is empty
+    for (int t = 1; t < VGLB_NUM_TIERS; t++)
+        if (g->tier_border[t] < g->tier_border[t - 1]) g->tier_border[t] = g->tier_border[t - 1];
+    g->tier_border[VGLB_NUM_TIERS - 1] = g->V;
+    g->max_degree = h[VGLB_NUM_TIERS];
+    return VGLB_OK;
+}
+
+static void graph_free_fields(vglb_graph *g)
+{
+    cudaFree(g->d_out_ptr); cudaFree(g->d_out_adj); cudaFree(g->d_in_ptr); cudaFree(g->d_in_adj);
+    cudaFree(g->d_fwd); cudaFree(g->d_bwd); cudaFree(g->d_edge_order);
+    cudaFree(g->d_pr_inv); cudaFree(g->d_pr_contrib[0]); cudaFree(g->d_pr_contrib[1]); cudaFree(g->d_pr_dangling);
+    cudaFree(g->d_visited); cudaFree(g->d_front_bm[0]); cudaFree(g->d_front_bm[1]);
+    cudaFree(g->d_queue[0]); cudaFree(g->d_queue[1]); cudaFree(g->d_scratch_i32);
+}
+
+extern "C" int vglb_graph_free(vglb_ctx *ctx, vglb_graph *g)
+{
+    VGLB_REQUIRE(ctx != NULL, "vglb_graph_free: ctx is NULL");
+    if (!g) return VGLB_OK;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    graph_free_fields(g);
+    cudaGetLastError();
+    free(g);
+    return VGLB_OK;
+}
+
+#define BUILD_TRY(call)                   \
+    do                                    \
+    {                                     \
+        int rc__ = (call);                \
+        if (rc__ != VGLB_OK)              \
+        {                                 \
+            cleanup();                    \
+            return rc__;                  \
+        }                                 \
+    } while (0)
+
+#define BUILD_CUDA(call)                                                                                   \
+    do                                                                                                     \
+    {                                                                                                      \
+        cudaError_t err__ = (call);                                                                        \
+        if (err__ != cudaSuccess)                                                                          \
+        {                                                                                                  \
+            vglb_set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(err__), __FILE__, __LINE__,   \
+                           #call);                                                                         \
+            cudaGetLastError();                                                                            \
+            cleanup();                                                                                     \
+            return err__ == cudaErrorMemoryAllocation ? VGLB_ENOMEM : VGLB_ECUDA;                          \
+        }                                                                                                  \
+    } while (0)
+
+// one direction: stable sort of the edges by fwd[key_ids], adjacency = fwd[other_ids] in that order
+static int build_direction(vglb_ctx *ctx, int32_t V, int64_t E, const int32_t *d_key_ids, const int32_t *d_other_ids,
+                           const int32_t *d_fwd, int32_t *d_adj, int64_t *d_edge_order)
+{
+    uint32_t *k0 = NULL, *k1 = NULL, *v0 = NULL, *v1 = NULL;
+    void *tmp = NULL;
+    auto cleanup = [&]() { cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1); cudaFree(tmp); };
+    if (E == 0) return VGLB_OK;
+    const size_t eb = (size_t)E * sizeof(uint32_t);
+    BUILD_CUDA(cudaMalloc(&k0, eb)); BUILD_CUDA(cudaMalloc(&k1, eb));
+    BUILD_CUDA(cudaMalloc(&v0, eb)); BUILD_CUDA(cudaMalloc(&v1, eb));
+    const int grid = ctx->sm_count * 16;
+    edge_keys_kernel<<<grid, 256, 0, ctx->stream>>>(d_key_ids, d_fwd, E, k0, v0);
+    BUILD_CUDA(cudaGetLastError());
+    cub::DoubleBuffer<uint32_t> keys(k0, k1), vals(v0, v1);
+    size_t tmp_bytes = 0;
+    BUILD_CUDA(cub::DeviceRadixSort::SortPairs(NULL, tmp_bytes, keys, vals, E, 0, bits_for(V), ctx->stream));
+    BUILD_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+    BUILD_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, vals, E, 0, bits_for(V), ctx->stream));
+    gather_adj_kernel<<<grid, 256, 0, ctx->stream>>>(vals.Current(), d_other_ids, d_fwd, E, d_adj, d_edge_order);
+    BUILD_CUDA(cudaGetLastError());
+    BUILD_CUDA(cudaStreamSynchronize(ctx->stream));
+    cleanup();
+    return VGLB_OK;
+}
+
+extern "C" int vglb_graph_from_edges(vglb_ctx *ctx, int32_t V, int64_t E, const int32_t *src, const int32_t *dst,
+                                     int src_on_device, int flags, vglb_graph **out_graph)
+{
+    VGLB_REQUIRE(ctx != NULL && out_graph != NULL, "vglb_graph_from_edges: NULL argument");
+    VGLB_REQUIRE(V > 0 && E >= 0 && E < 0xFFFFFFFFLL, "vglb_graph_from_edges: need V > 0 and 0 <= E < 2^32-1 per device");
+    VGLB_REQUIRE(E == 0 || (src != NULL && dst != NULL), "vglb_graph_from_edges: NULL edge arrays");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    vglb_graph *g = (vglb_graph *)calloc(1, sizeof(vglb_graph));
+    if (!g) return VGLB_ENOMEM;
+    g->V = V;
+    g->E = E;
+    int32_t *d_src_own = NULL, *d_dst_own = NULL, *d_deg = NULL;
+    uint32_t *dk0 = NULL, *dk1 = NULL, *dv0 = NULL, *dv1 = NULL;
+    int64_t *d_deg_sorted = NULL;
+    void *tmp = NULL;
+    int *d_bad = NULL;
+    auto cleanup = [&]() {
+        cudaFree(d_src_own); cudaFree(d_dst_own); cudaFree(d_deg); cudaFree(dk0); cudaFree(dk1); cudaFree(dv0);
+        cudaFree(dv1); cudaFree(d_deg_sorted); cudaFree(tmp); cudaFree(d_bad);
+        graph_free_fields(g);
+        free(g);
+    };
+    const int32_t *d_src = src, *d_dst = dst;
+    const size_t eb = (size_t)(E ? E : 1) * sizeof(int32_t);
+    if (!src_on_device)
+    {
+        BUILD_CUDA(cudaMalloc(&d_src_own, eb));
+        BUILD_CUDA(cudaMalloc(&d_dst_own, eb));
+        BUILD_CUDA(cudaMemcpyAsync(d_src_own, src, (size_t)E * 4, cudaMemcpyHostToDevice, ctx->stream));
+        BUILD_CUDA(cudaMemcpyAsync(d_dst_own, dst, (size_t)E * 4, cudaMemcpyHostToDevice, ctx->stream));
+        d_src = d_src_own;
+        d_dst = d_dst_own;
+    }
+    const int grid = ctx->sm_count * 16;
+    const unsigned vgrid = (unsigned)ceil_div64((int64_t)V + 1, 256);
+
+    // 1. out-degree histogram (extract_connection_count)
+    BUILD_CUDA(cudaMalloc(&d_deg, (size_t)V * 4));
+    BUILD_CUDA(cudaMalloc(&d_bad, 4));
+    BUILD_CUDA(cudaMemsetAsync(d_deg, 0, (size_t)V * 4, ctx->stream));
+    BUILD_CUDA(cudaMemsetAsync(d_bad, 0, 4, ctx->stream));
+    if (E)
+    {
+        degree_histogram_kernel<<<grid, 256, 0, ctx->stream>>>(d_src, E, V, d_deg, d_bad);
+        BUILD_CUDA(cudaGetLastError());
+        range_check_kernel<<<grid, 256, 0, ctx->stream>>>(d_dst, E, V, d_bad);
+        BUILD_CUDA(cudaGetLastError());
+    }
+    int bad = 0;
+    BUILD_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    BUILD_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (bad)
+    {
+        vglb_set_error("vglb_graph_from_edges: vertex id out of range [0, V)");
+        cleanup();
+        return VGLB_EINVAL;
+    }
+    // 2. stable sort of vertex ids by degree descending (sort_vertices_by_degree)
+    BUILD_CUDA(cudaMalloc(&dk0, (size_t)V * 4)); BUILD_CUDA(cudaMalloc(&dk1, (size_t)V * 4));
+    BUILD_CUDA(cudaMalloc(&dv0, (size_t)V * 4)); BUILD_CUDA(cudaMalloc(&dv1, (size_t)V * 4));
+    degree_sort_keys_kernel<<<vgrid, 256, 0, ctx->stream>>>(d_deg, V, dk0, dv0);
+    BUILD_CUDA(cudaGetLastError());
+    {
+        cub::DoubleBuffer<uint32_t> keys(dk0, dk1), vals(dv0, dv1);
+        size_t tmp_bytes = 0;
+        BUILD_CUDA(cub::DeviceRadixSort::SortPairs(NULL, tmp_bytes, keys, vals, V, 0, 32, ctx->stream));
+        BUILD_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+        BUILD_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, vals, V, 0, 32, ctx->stream));
+        BUILD_CUDA(cudaMalloc(&g->d_fwd, (size_t)V * 4));
+        BUILD_CUDA(cudaMalloc(&g->d_bwd, (size_t)V * 4));
+        BUILD_CUDA(cudaMalloc(&d_deg_sorted, ((size_t)V + 1) * 8));
+        conversions_kernel<<<vgrid, 256, 0, ctx->stream>>>(vals.Current(), d_deg, V, g->d_fwd, g->d_bwd, d_deg_sorted);
+        BUILD_CUDA(cudaGetLastError());
+        BUILD_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(tmp); tmp = NULL;
+    }
+    cudaFree(dk0); cudaFree(dk1); cudaFree(dv0); cudaFree(dv1);
+    dk0 = dk1 = dv0 = dv1 = NULL;
+    // 3. row pointers (construct_CSR)
+    BUILD_CUDA(cudaMalloc(&g->d_out_ptr, ((size_t)V + 2) * 8));
+    {
+        size_t tmp_bytes = 0;
+        BUILD_CUDA(cub::DeviceScan::ExclusiveSum(NULL, tmp_bytes, d_deg_sorted, g->d_out_ptr, V + 1, ctx->stream));
+        BUILD_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+        BUILD_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_deg_sorted, g->d_out_ptr, V + 1, ctx->stream));
+        BUILD_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(tmp); tmp = NULL;
+    }
+    // 4. edges: stable sort by new src id, adjacency in new ids (renumber + preprocess_into_csr_based)
+    BUILD_CUDA(cudaMalloc(&g->d_out_adj, eb + 16));
+    if (flags & VGLB_GRAPH_WITH_EDGE_ORDER) BUILD_CUDA(cudaMalloc(&g->d_edge_order, (size_t)(E ? E : 1) * 8));
+    BUILD_TRY(build_direction(ctx, V, E, d_src, d_dst, g->d_fwd, g->d_out_adj, g->d_edge_order));
+    // 5. incoming CSR on the same numbering
+    if (flags & VGLB_GRAPH_WITH_INCOMING)
+    {
+        BUILD_CUDA(cudaMemsetAsync(d_deg_sorted, 0, ((size_t)V + 1) * 8, ctx->stream));
+        if (E)
+        {
+            indegree_sorted_kernel<<<grid, 256, 0, ctx->stream>>>(d_dst, g->d_fwd, E, (unsigned long long *)d_deg_sorted);
+            BUILD_CUDA(cudaGetLastError());
+        }
+        BUILD_CUDA(cudaMalloc(&g->d_in_ptr, ((size_t)V + 2) * 8));
+        size_t tmp_bytes = 0;
+        BUILD_CUDA(cub::DeviceScan::ExclusiveSum(NULL, tmp_bytes, d_deg_sorted, g->d_in_ptr, V + 1, ctx->stream));
+        BUILD_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+        BUILD_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_deg_sorted, g->d_in_ptr, V + 1, ctx->stream));
+        BUILD_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(tmp); tmp = NULL;
+        BUILD_CUDA(cudaMalloc(&g->d_in_adj, eb + 16));
+        BUILD_TRY(build_direction(ctx, V, E, d_dst, d_src, g->d_fwd, g->d_in_adj, NULL));
+    }
+    BUILD_TRY(vglb_graph_compute_tiers(ctx, g));
+    cudaFree(d_src_own); cudaFree(d_dst_own); cudaFree(d_deg); cudaFree(d_deg_sorted); cudaFree(d_bad);
+    *out_graph = g;
+    return VGLB_OK;
+}
+
+extern "C" int vglb_graph_from_csr(vglb_ctx *ctx, int32_t V, int64_t E, const int64_t *h_out_ptr,
+                                   const int32_t *h_out_adj, const int32_t *h_orig_to_sorted, const int64_t *h_in_ptr,
+                                   const int32_t *h_in_adj, vglb_graph **out_graph)
+{
+    VGLB_REQUIRE(ctx != NULL && out_graph != NULL && h_out_ptr != NULL, "vglb_graph_from_csr: NULL argument");
+    VGLB_REQUIRE(V > 0 && E >= 0 && (E == 0 || h_out_adj != NULL), "vglb_graph_from_csr: bad sizes");
+    VGLB_REQUIRE((h_in_ptr == NULL) == (h_in_adj == NULL) || E == 0, "vglb_graph_from_csr: incoming arrays must come together");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    vglb_graph *g = (vglb_graph *)calloc(1, sizeof(vglb_graph));
+    if (!g) return VGLB_ENOMEM;
+    g->V = V;
+    g->E = E;
+    auto cleanup = [&]() { graph_free_fields(g); free(g); };
+    const size_t eb = (size_t)(E ? E : 1) * 4;
+    BUILD_CUDA(cudaMalloc(&g->d_out_ptr, ((size_t)V + 2) * 8));
+    BUILD_CUDA(cudaMalloc(&g->d_out_adj, eb + 16));
+    BUILD_CUDA(cudaMemcpyAsync(g->d_out_ptr, h_out_ptr, ((size_t)V + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    BUILD_CUDA(cudaMemcpyAsync(g->d_out_adj, h_out_adj, (size_t)E * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (h_in_ptr)
+    {
+        BUILD_CUDA(cudaMalloc(&g->d_in_ptr, ((size_t)V + 2) * 8));
+        BUILD_CUDA(cudaMalloc(&g->d_in_adj, eb + 16));
+        BUILD_CUDA(cudaMemcpyAsync(g->d_in_ptr, h_in_ptr, ((size_t)V + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        BUILD_CUDA(cudaMemcpyAsync(g->d_in_adj, h_in_adj, (size_t)E * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    BUILD_CUDA(cudaMalloc(&g->d_fwd, (size_t)V * 4));
+    BUILD_CUDA(cudaMalloc(&g->d_bwd, (size_t)V * 4));
+    const unsigned vgrid = (unsigned)ceil_div64(V, 256);
+    if (h_orig_to_sorted)
+        BUILD_CUDA(cudaMemcpyAsync(g->d_fwd, h_orig_to_sorted, (size_t)V * 4, cudaMemcpyHostToDevice, ctx->stream));
+    else
+    {
+        iota_kernel<<<vgrid, 256, 0, ctx->stream>>>(g->d_fwd, V);
+        BUILD_CUDA(cudaGetLastError());
+    }
+    invert_perm_kernel<<<vgrid, 256, 0, ctx->stream>>>(g->d_fwd, g->d_bwd, V);
+    BUILD_CUDA(cudaGetLastError());
+    BUILD_TRY(vglb_graph_compute_tiers(ctx, g));
+    *out_graph = g;
+    return VGLB_OK;
+}
+
+extern "C" int vglb_graph_get_info(vglb_graph *g, vglb_graph_info *info)
+{
+    VGLB_REQUIRE(g != NULL && info != NULL, "vglb_graph_get_info: NULL argument");
+    memset(info, 0, sizeof(*info));
+    info->vertices = g->V;
+    info->edges = g->E;
+    info->has_incoming = g->d_in_ptr != NULL;
+    info->max_degree = g->max_degree;
+    for (int t = 0; t < VGLB_NUM_TIERS; t++)
+    {
+        info->tier_degree[t] = g->tier_degree[t];
+        info->tier_border[t] = g->tier_border[t];
+    }
+    info->d_out_ptr = g->d_out_ptr;
+    info->d_out_adj = g->d_out_adj;
+    info->d_in_ptr = g->d_in_ptr;
+    info->d_in_adj = g->d_in_adj;
+    info->d_orig_to_sorted = g->d_fwd;
+    info->d_sorted_to_orig = g->d_bwd;
+    info->d_edge_order = g->d_edge_order;
+    return VGLB_OK;
+}
+
+// ---- estimate_thresholds twin for an arbitrary threshold -------------------------------------------------------------
+
+__global__ void threshold_vertex_kernel(const int64_t *__restrict__ ptr, int32_t V, int32_t T, int32_t *out)
+{
+    int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const int64_t d = ptr[v + 1] - ptr[v];
+    const int64_t dn = (v == V - 1) ? -1 : ptr[v + 2] - ptr[v + 1];
+    if (d >= T && dn < T) *out = v + 1;
+}
+
+extern "C" int vglb_graph_threshold_vertex(vglb_ctx *ctx, vglb_graph *g, int32_t degree_threshold, int32_t *out_vertex)
+{
+    VGLB_REQUIRE(ctx != NULL && g != NULL && out_vertex != NULL, "vglb_graph_threshold_vertex: NULL argument");
+    int32_t *d_out = (int32_t *)ctx->d_counters;
+    CUDA_TRY(cudaMemsetAsync(d_out, 0, 4, ctx->stream));
+    threshold_vertex_kernel<<<(unsigned)ceil_div64(g->V, 256), 256, 0, ctx->stream>>>(g->d_out_ptr, g->V, degree_threshold, d_out);
+    KERNEL_TRY();
+    CUDA_TRY(cudaMemcpyAsync(out_vertex, d_out, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(d_out, 0, 4, ctx->stream));
+    return VGLB_OK;
+}
+
+// ---- VerticesArray::reorder (vgl_graph/reorder.hpp:3-170, cuda_reorder.cu:5-37): one out-of-place gather ------------
+
+__global__ void reorder_gather_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
+                                      const int32_t *__restrict__ index, int32_t V)
+{
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < V) out[i] = in[index[i]];
+}
+
+extern "C" int vglb_varray_reorder_u32(vglb_ctx *ctx, vglb_graph *g, const uint32_t *d_in, uint32_t *d_out, int from_dir,
+                                       int to_dir)
+{
+    VGLB_REQUIRE(ctx != NULL && g != NULL && d_in != NULL && d_out != NULL, "vglb_varray_reorder_u32: NULL argument");
+    VGLB_REQUIRE(d_in != (const uint32_t *)d_out, "vglb_varray_reorder_u32: reorder is out-of-place");
+    const int32_t *index = NULL;
+    if (from_dir == VGLB_SCATTER && to_dir == VGLB_ORIGINAL) index = g->d_fwd;       // out[orig] = in[fwd[orig]]
+    else if (from_dir == VGLB_ORIGINAL && to_dir == VGLB_SCATTER) index = g->d_bwd;  // out[sorted] = in[bwd[sorted]]
+    else
+    {
+        vglb_set_error("vglb_varray_reorder_u32: only ORIGINAL <-> SCATTER is supported on the device layout "
+                       "(the incoming CSR shares the SCATTER numbering)");
+        return VGLB_EINVAL;
+    }
+    reorder_gather_kernel<<<(unsigned)ceil_div64(g->V, 256), 256, 0, ctx->stream>>>(d_in, d_out, index, g->V);
+    KERNEL_TRY();
+    ctx->launches++;
+    return VGLB_OK;
+}
+
+// ---- EdgesArray synthetic weights (EdgesArray::set_all_random twin, deterministic) ---------------------------------
+
+__global__ void fill_weights_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj,
+                                    const int32_t *__restrict__ bwd, int32_t V, uint64_t seed, float *__restrict__ w)
+{
+    // warp per row, lanes stride the row
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t v = warp; v < V; v += nwarps)
+    {
+        const int64_t s = ptr[v], e = ptr[v + 1];
+        const int32_t ov = bwd[v];
+        for (int64_t p = s + lane_id(); p < e; p += 32) w[p] = vglb_edge_weight(ov, bwd[adj[p]], seed);
+    }
+}
+
+extern "C" int vglb_earray_fill_synthetic_weights(vglb_ctx *ctx, vglb_graph *g, uint64_t seed, float *d_weights)
+{
+    VGLB_REQUIRE(ctx != NULL && g != NULL && d_weights != NULL, "vglb_earray_fill_synthetic_weights: NULL argument");
+    fill_weights_kernel<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(g->d_out_ptr, g->d_out_adj, g->d_bwd, g->V, seed, d_weights);
+    KERNEL_TRY();
+    ctx->launches++;
+    return VGLB_OK;
+}
+
+// ---- in-degree without self loops on the SCATTER numbering (pr.hpp:28-73) --------------------------------------------
+
+__global__ void indegree_noloops_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, int32_t V,
+                                        int32_t *__restrict__ indeg)
+{
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t v = warp; v < V; v += nwarps)
+    {
+        const int64_t s = ptr[v], e = ptr[v + 1];
+        for (int64_t p = s + lane_id(); p < e; p += 32)
+        {
+            const int32_t d = adj[p];
+            if (d != (int32_t)v) atomicAdd(&indeg[d], 1);
+        }
+    }
+}
+
+extern "C" int vglb_graph_indegree_noloops(vglb_ctx *ctx, vglb_graph *g, int32_t *d_indeg)
+{
+    VGLB_REQUIRE(ctx != NULL && g != NULL && d_indeg != NULL, "vglb_graph_indegree_noloops: NULL argument");
+    CUDA_TRY(cudaMemsetAsync(d_indeg, 0, (size_t)g->V * 4, ctx->stream));
+    indegree_noloops_kernel<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(g->d_out_ptr, g->d_out_adj, g->V, d_indeg);
+    KERNEL_TRY();
+    ctx->launches++;
+    return VGLB_OK;
+}
