@@ -88,7 +88,8 @@ struct vglb_frontier
     int32_t tier_size[3];
     int32_t *d_ids;
     uint32_t *d_bitmap;
-    int32_t *d_block_counts;
+    void *d_tile_status;   // [8 counters][one look-back status word per GNF tile]
+    int64_t tiles;
 };
 
 // degree thresholds of the tiers: tier t holds rows with degree in [tier_degree[t], tier_degree[t-1]).
@@ -102,7 +103,6 @@ constexpr int32_t vglb_tier_degree(int t)
 }
 
 int vglb_graph_compute_tiers(vglb_ctx *ctx, vglb_graph *g);
-int vglb_graph_alloc_common(vglb_ctx *ctx, vglb_graph *g);
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

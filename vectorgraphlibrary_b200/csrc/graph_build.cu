@@ -219,9 +219,10 @@ extern "C" int vglb_graph_free(vglb_ctx *ctx, vglb_graph *g)
         }                                                                                                  \
     } while (0)
 
-// one direction: stable sort of the edges by fwd[key_ids], adjacency = fwd[other_ids] in that order
-static int build_direction(vglb_ctx *ctx, int32_t V, int64_t E, const int32_t *d_key_ids, const int32_t *d_other_ids,
-                           const int32_t *d_fwd, int32_t *d_adj, int64_t *d_edge_order)
+// outgoing direction: stable sort of the edges by fwd[src]; adjacency = fwd[dst] in that order. When d_row_of_pos is
+// non-NULL it receives the (ascending) row id of every CSR position, which the incoming build reuses.
+static int build_outgoing(vglb_ctx *ctx, int32_t V, int64_t E, const int32_t *d_src, const int32_t *d_dst,
+                          const int32_t *d_fwd, int32_t *d_adj, int64_t *d_edge_order, uint32_t *d_row_of_pos)
 {
     uint32_t *k0 = NULL, *k1 = NULL, *v0 = NULL, *v1 = NULL;
     void *tmp = NULL;
@@ -231,15 +232,41 @@ static int build_direction(vglb_ctx *ctx, int32_t V, int64_t E, const int32_t *d
     BUILD_CUDA(cudaMalloc(&k0, eb)); BUILD_CUDA(cudaMalloc(&k1, eb));
     BUILD_CUDA(cudaMalloc(&v0, eb)); BUILD_CUDA(cudaMalloc(&v1, eb));
     const int grid = ctx->sm_count * 16;
-    edge_keys_kernel<<<grid, 256, 0, ctx->stream>>>(d_key_ids, d_fwd, E, k0, v0);
+    edge_keys_kernel<<<grid, 256, 0, ctx->stream>>>(d_src, d_fwd, E, k0, v0);
     BUILD_CUDA(cudaGetLastError());
     cub::DoubleBuffer<uint32_t> keys(k0, k1), vals(v0, v1);
     size_t tmp_bytes = 0;
     BUILD_CUDA(cub::DeviceRadixSort::SortPairs(NULL, tmp_bytes, keys, vals, E, 0, bits_for(V), ctx->stream));
     BUILD_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
     BUILD_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, vals, E, 0, bits_for(V), ctx->stream));
-    gather_adj_kernel<<<grid, 256, 0, ctx->stream>>>(vals.Current(), d_other_ids, d_fwd, E, d_adj, d_edge_order);
+    gather_adj_kernel<<<grid, 256, 0, ctx->stream>>>(vals.Current(), d_dst, d_fwd, E, d_adj, d_edge_order);
     BUILD_CUDA(cudaGetLastError());
+    if (d_row_of_pos)
+        BUILD_CUDA(cudaMemcpyAsync(d_row_of_pos, keys.Current(), eb, cudaMemcpyDeviceToDevice, ctx->stream));
+    BUILD_CUDA(cudaStreamSynchronize(ctx->stream));
+    cleanup();
+    return VGLB_OK;
+}
+
+// incoming direction on the SAME numbering: stable sort of the out-CSR positions by destination. Because the
+// positions are already ordered by source id, every in-row lists its sources in ascending id = descending out-degree
+// (hubs first), which is what makes the bottom-up early exit short. d_row_of_pos is consumed (becomes in_adj).
+static int build_incoming(vglb_ctx *ctx, int32_t V, int64_t E, const int32_t *d_out_adj, uint32_t *d_row_of_pos,
+                          int32_t *d_in_adj)
+{
+    uint32_t *k0 = NULL, *k1 = NULL, *v1 = NULL;
+    void *tmp = NULL;
+    auto cleanup = [&]() { cudaFree(k0); cudaFree(k1); cudaFree(v1); cudaFree(tmp); };
+    if (E == 0) return VGLB_OK;
+    const size_t eb = (size_t)E * sizeof(uint32_t);
+    BUILD_CUDA(cudaMalloc(&k0, eb)); BUILD_CUDA(cudaMalloc(&k1, eb)); BUILD_CUDA(cudaMalloc(&v1, eb));
+    BUILD_CUDA(cudaMemcpyAsync(k0, d_out_adj, eb, cudaMemcpyDeviceToDevice, ctx->stream));
+    cub::DoubleBuffer<uint32_t> keys(k0, k1), vals(d_row_of_pos, v1);
+    size_t tmp_bytes = 0;
+    BUILD_CUDA(cub::DeviceRadixSort::SortPairs(NULL, tmp_bytes, keys, vals, E, 0, bits_for(V), ctx->stream));
+    BUILD_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+    BUILD_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, vals, E, 0, bits_for(V), ctx->stream));
+    BUILD_CUDA(cudaMemcpyAsync(d_in_adj, vals.Current(), eb, cudaMemcpyDeviceToDevice, ctx->stream));
     BUILD_CUDA(cudaStreamSynchronize(ctx->stream));
     cleanup();
     return VGLB_OK;
@@ -257,13 +284,13 @@ extern "C" int vglb_graph_from_edges(vglb_ctx *ctx, int32_t V, int64_t E, const 
     g->V = V;
     g->E = E;
     int32_t *d_src_own = NULL, *d_dst_own = NULL, *d_deg = NULL;
-    uint32_t *dk0 = NULL, *dk1 = NULL, *dv0 = NULL, *dv1 = NULL;
+    uint32_t *dk0 = NULL, *dk1 = NULL, *dv0 = NULL, *dv1 = NULL, *d_row_of_pos = NULL;
     int64_t *d_deg_sorted = NULL;
     void *tmp = NULL;
     int *d_bad = NULL;
     auto cleanup = [&]() {
         cudaFree(d_src_own); cudaFree(d_dst_own); cudaFree(d_deg); cudaFree(dk0); cudaFree(dk1); cudaFree(dv0);
-        cudaFree(dv1); cudaFree(d_deg_sorted); cudaFree(tmp); cudaFree(d_bad);
+        cudaFree(dv1); cudaFree(d_deg_sorted); cudaFree(tmp); cudaFree(d_bad); cudaFree(d_row_of_pos);
         graph_free_fields(g);
         free(g);
     };
@@ -336,7 +363,8 @@ extern "C" int vglb_graph_from_edges(vglb_ctx *ctx, int32_t V, int64_t E, const 
     // 4. edges: stable sort by new src id, adjacency in new ids (renumber + preprocess_into_csr_based)
     BUILD_CUDA(cudaMalloc(&g->d_out_adj, eb + 16));
     if (flags & VGLB_GRAPH_WITH_EDGE_ORDER) BUILD_CUDA(cudaMalloc(&g->d_edge_order, (size_t)(E ? E : 1) * 8));
-    BUILD_TRY(build_direction(ctx, V, E, d_src, d_dst, g->d_fwd, g->d_out_adj, g->d_edge_order));
+    if ((flags & VGLB_GRAPH_WITH_INCOMING) && E) BUILD_CUDA(cudaMalloc(&d_row_of_pos, eb));
+    BUILD_TRY(build_outgoing(ctx, V, E, d_src, d_dst, g->d_fwd, g->d_out_adj, g->d_edge_order, d_row_of_pos));
     // 5. incoming CSR on the same numbering
     if (flags & VGLB_GRAPH_WITH_INCOMING)
     {
@@ -354,10 +382,11 @@ extern "C" int vglb_graph_from_edges(vglb_ctx *ctx, int32_t V, int64_t E, const 
         BUILD_CUDA(cudaStreamSynchronize(ctx->stream));
         cudaFree(tmp); tmp = NULL;
         BUILD_CUDA(cudaMalloc(&g->d_in_adj, eb + 16));
-        BUILD_TRY(build_direction(ctx, V, E, d_dst, d_src, g->d_fwd, g->d_in_adj, NULL));
+        BUILD_TRY(build_incoming(ctx, V, E, g->d_out_adj, d_row_of_pos, g->d_in_adj));
     }
     BUILD_TRY(vglb_graph_compute_tiers(ctx, g));
     cudaFree(d_src_own); cudaFree(d_dst_own); cudaFree(d_deg); cudaFree(d_deg_sorted); cudaFree(d_bad);
+    cudaFree(d_row_of_pos);
     *out_graph = g;
     return VGLB_OK;
 }
