@@ -62,6 +62,7 @@ int vglb_malloc(vglb_ctx *ctx, size_t bytes, void **d_ptr);
 int vglb_free(vglb_ctx *ctx, void *d_ptr);
 int vglb_memcpy_h2d(vglb_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
 int vglb_memcpy_d2h(vglb_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+int vglb_memcpy_d2d(vglb_ctx *ctx, void *d_dst, const void *d_src, size_t bytes);
 int vglb_memset(vglb_ctx *ctx, void *d_dst, int byte_value, size_t bytes);
 int vglb_host_alloc_pinned(size_t bytes, void **h_ptr);
 int vglb_host_free_pinned(void *h_ptr);

@@ -74,6 +74,7 @@ _SIGNATURES = {
     "vglb_free": (C.c_int, [_P, _P]),
     "vglb_memcpy_h2d": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "vglb_memcpy_d2h": (C.c_int, [_P, _P, _P, C.c_size_t]),
+    "vglb_memcpy_d2d": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "vglb_memset": (C.c_int, [_P, _P, C.c_int, C.c_size_t]),
     "vglb_host_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
     "vglb_host_free_pinned": (C.c_int, [_P]),
@@ -141,6 +142,16 @@ def generate_edges_host(kind: int, scale: int, edge_factor: int, seed: int = MAS
     src, dst = np.empty(E, np.int32), np.empty(E, np.int32)
     _check(lib().vglb_generate_edges_host(kind, scale, E, seed, abc[0], abc[1], abc[2], src.ctypes.data, dst.ctypes.data))
     return src, dst
+
+
+def pinned_array(n: int, dtype):
+    """numpy view of pinned host memory (vglb_host_alloc_pinned); lives until the process exits."""
+    dtype = np.dtype(dtype)
+    nbytes = max(1, int(n)) * dtype.itemsize
+    p = _P()
+    _check(lib().vglb_host_alloc_pinned(nbytes, C.byref(p)))
+    buf = (C.c_char * nbytes).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype, count=int(n))
 
 
 class Context:

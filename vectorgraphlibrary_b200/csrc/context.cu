@@ -121,6 +121,13 @@ extern "C" int vglb_memcpy_d2h(vglb_ctx *ctx, void *h_dst, const void *d_src, si
     return VGLB_OK;
 }
 
+extern "C" int vglb_memcpy_d2d(vglb_ctx *ctx, void *d_dst, const void *d_src, size_t bytes)
+{
+    VGLB_REQUIRE(ctx != NULL, "vglb_memcpy_d2d: ctx is NULL");
+    CUDA_TRY(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return VGLB_OK;
+}
+
 extern "C" int vglb_memset(vglb_ctx *ctx, void *d_dst, int byte_value, size_t bytes)
 {
     VGLB_REQUIRE(ctx != NULL, "vglb_memset: ctx is NULL");
