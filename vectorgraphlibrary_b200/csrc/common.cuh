@@ -72,6 +72,8 @@ struct vglb_graph
     float *d_pr_contrib[2];
     double *d_pr_dangling; // one slot per sweep
     int pr_dangling_slots;
+    int32_t *d_pr_chunk_row; // chunk table of the PageRank sweep (pagerank.cu)
+    int32_t pr_big_rows, pr_chunks;
     // BFS / SSSP / CC scratch
     uint32_t *d_visited, *d_front_bm[2];
     int32_t *d_queue[2];
