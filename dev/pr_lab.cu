@@ -268,6 +268,111 @@ __global__ void dsmem_kernel(const int4 *__restrict__ adj4, int64_t n4, const fl
     cluster.sync();
 }
 
+// tile-per-CTA: gather phase (flat, coalesced int4, U vectors per thread) -> values staged in shared memory -> reduction
+// phase over fake rows of DEG consecutive edges, G lanes per row (stands in for the segmented reduction)
+template <int U, int DEG, int G>
+__global__ void __launch_bounds__(256) staged_kernel(const int4 *__restrict__ adj4, int64_t n4, const float *__restrict__ c,
+                                                     float *__restrict__ out)
+{
+    constexpr int T = 256 * U * 4;
+    __shared__ __align__(16) float s_val[T];
+    const int64_t q0 = (int64_t)blockIdx.x * (256 * U);
+    int4 a[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) a[u] = q0 + u * 256 + threadIdx.x < n4 ? ld_stream_v4(adj4 + q0 + u * 256 + threadIdx.x) : make_int4(0, 0, 0, 0);
+    float4 f[U];
+#pragma unroll
+    for (int u = 0; u < U; u++)
+    {
+        f[u].x = ld_nc(c + a[u].x); f[u].y = ld_nc(c + a[u].y); f[u].z = ld_nc(c + a[u].z); f[u].w = ld_nc(c + a[u].w);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) reinterpret_cast<float4 *>(s_val)[u * 256 + threadIdx.x] = f[u];
+    __syncthreads();
+    constexpr int ROWS = T / DEG;
+    const int gid = threadIdx.x / G, gl = threadIdx.x % G;
+    for (int r = gid; r < ROWS; r += 256 / G)
+    {
+        float acc = 0.f;
+        for (int j = gl; j < DEG; j += G) acc += s_val[r * DEG + j];
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (gl == 0) out[(int64_t)blockIdx.x * ROWS + r] = acc;
+    }
+}
+
+// the same, persistent: grid = resident CTAs, each looping over tiles with stride gridDim.x
+template <int U, int DEG, int G, int STAGE>
+__global__ void __launch_bounds__(256) staged_persistent_kernel(const int4 *__restrict__ adj4, int64_t n4, const float *__restrict__ c,
+                                                                float *__restrict__ out)
+{
+    constexpr int T = 256 * U * 4;
+    __shared__ __align__(16) float s_val[STAGE ? T : 4];
+    const int64_t ntiles = (n4 + 256 * U - 1) / (256 * U);
+    float keep = 0.f;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+    {
+        const int64_t q0 = tile * (256 * U);
+        int4 a[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) a[u] = q0 + u * 256 + threadIdx.x < n4 ? ld_stream_v4(adj4 + q0 + u * 256 + threadIdx.x) : make_int4(0, 0, 0, 0);
+        float4 f[U];
+#pragma unroll
+        for (int u = 0; u < U; u++)
+        {
+            f[u].x = ld_nc(c + a[u].x); f[u].y = ld_nc(c + a[u].y); f[u].z = ld_nc(c + a[u].z); f[u].w = ld_nc(c + a[u].w);
+        }
+        if (STAGE)
+        {
+#pragma unroll
+            for (int u = 0; u < U; u++) reinterpret_cast<float4 *>(s_val)[u * 256 + threadIdx.x] = f[u];
+            __syncthreads();
+            constexpr int ROWS = T / DEG;
+            const int gid = threadIdx.x / G, gl = threadIdx.x % G;
+            for (int r = gid; r < ROWS; r += 256 / G)
+            {
+                float acc = 0.f;
+                for (int j = gl; j < DEG; j += G) acc += s_val[r * DEG + j];
+#pragma unroll
+                for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (gl == 0) out[tile * ROWS + r] = acc;
+            }
+            __syncthreads();
+        }
+        else
+        {
+#pragma unroll
+            for (int u = 0; u < U; u++) keep += (f[u].x + f[u].y) + (f[u].z + f[u].w);
+        }
+    }
+    if (!STAGE) out[(int64_t)blockIdx.x * 256 + threadIdx.x] = keep;
+}
+
+template <int U, int DEG, int G, int STAGE>
+static void run_staged_persistent(const int32_t *adj, int64_t E, const float *c, float *d_out, int ctas_per_sm)
+{
+    const int64_t n4 = E / 4;
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, staged_persistent_kernel<U, DEG, G, STAGE>, 256, 0));
+    const int per_sm = ctas_per_sm > 0 ? std::min(occ, ctas_per_sm) : 0;
+    const int64_t ntiles = (n4 + 256 * U - 1) / (256 * U);
+    const int grid = per_sm > 0 ? 148 * per_sm : (int)ntiles;
+    const float ms = time_ms([&] { staged_persistent_kernel<U, DEG, G, STAGE><<<grid, 256>>>((const int4 *)adj, n4, c, d_out); });
+    printf("%s tile %5d edges, rows of %4d, %2d lanes/row, grid %6d (%d/SM, occ %d) : %8.3f ms  %7.1f Gedge/s\n",
+           STAGE ? "PERSIST-STAGED" : "PERSIST-NOSTAGE", 256 * U * 4, DEG, G, grid, per_sm, occ, ms, E / ms * 1e-6);
+    fflush(stdout);
+}
+
+template <int U, int DEG, int G>
+static void run_staged(const int32_t *adj, int64_t E, const float *c, float *d_out)
+{
+    const int64_t n4 = E / 4;
+    const int grid = (int)((n4 + 256 * U - 1) / (256 * U));
+    const float ms = time_ms([&] { staged_kernel<U, DEG, G><<<grid, 256>>>((const int4 *)adj, n4, c, d_out); });
+    printf("STAGED tile %5d edges, fake rows of %4d, %2d lanes/row : %8.3f ms  %7.1f Gedge/s\n", 256 * U * 4, DEG, G, ms, E / ms * 1e-6);
+    fflush(stdout);
+}
+
 __global__ void fill_random_kernel(float *c, int64_t n)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -359,7 +464,7 @@ int main(int argc, char **argv)
 
     float *c, *d_out;
     CK(cudaMalloc(&c, (size_t)V * 4));
-    CK(cudaMalloc(&d_out, (size_t)148 * 16 * 1024 * 4));
+    CK(cudaMalloc(&d_out, (size_t)E * 4 + (size_t)148 * 16 * 1024 * 4));
     fill_random_kernel<<<148 * 8, 256>>>(c, V);
     const int32_t *adj = info.d_out_adj;
 
@@ -376,24 +481,19 @@ int main(int argc, char **argv)
     }
 
 #define FLAT(MODE, U, H, T, C) run_flat<MODE, U>(#MODE, adj, E, c, V, H, T, C, d_out)
-    FLAT(M_LDG, 2, 0, 1024, 2);
-    FLAT(M_UNIFORM, 2, 0, 1024, 2);
-    FLAT(M_UNIPAIR, 2, 0, 1024, 2);
-    FLAT(M_UNIQUAD, 2, 0, 1024, 2);
-    FLAT(M_UNISAMESEC, 2, 0, 1024, 2);
-    FLAT(M_EVICT_SPLIT, 2, 16384, 1024, 2);
-    FLAT(M_EVICT_SPLIT, 2, 32768, 1024, 2);
-    FLAT(M_EVICT_SPLIT, 2, 49152, 1024, 2);
-    FLAT(M_EVICT_SPLIT, 2, 65536, 1024, 2);
-    FLAT(M_EVICT_SPLIT, 2, 98304, 1024, 2);
-    FLAT(M_EVICT_FIRST_COLD, 2, 32768, 1024, 2);
-    FLAT(M_EVICT_FIRST_COLD, 2, 49152, 1024, 2);
-    FLAT(M_EVICT_FIRST_COLD, 2, 65536, 1024, 2);
-    FLAT(M_NOALLOC_COLD, 2, 49152, 1024, 2);
-    FLAT(M_NOALLOC_COLD, 2, 196608, 1024, 2);
-    FLAT(M_NOALLOC_COLD, 2, 786432, 1024, 2);
-    FLAT(M_MIXED, 2, 24576, 1024, 2);
-    FLAT(M_MIXED, 2, 32768, 1024, 1);
+    FLAT(M_LDG, 2, 0, 256, 8);
+    run_staged<4, 128, 32>(adj, E, c, d_out);
+    run_staged_persistent<4, 128, 32, 0>(adj, E, c, d_out, 8);
+    run_staged_persistent<4, 128, 32, 0>(adj, E, c, d_out, 4);
+    run_staged_persistent<4, 128, 32, 0>(adj, E, c, d_out, 0);
+    run_staged_persistent<4, 128, 32, 1>(adj, E, c, d_out, 8);
+    run_staged_persistent<4, 128, 32, 1>(adj, E, c, d_out, 4);
+    run_staged_persistent<4, 128, 32, 1>(adj, E, c, d_out, 0);
+    run_staged_persistent<2, 128, 32, 0>(adj, E, c, d_out, 8);
+    run_staged_persistent<2, 128, 32, 1>(adj, E, c, d_out, 8);
+    run_staged_persistent<2, 128, 32, 0>(adj, E, c, d_out, 0);
+    run_staged_persistent<1, 128, 32, 0>(adj, E, c, d_out, 8);
+    run_staged_persistent<1, 128, 32, 0>(adj, E, c, d_out, 0);
     // partitioned chunks
     if (argc > 2)
     {

@@ -22,7 +22,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvgl_b200.so")
+LIB_PATH = os.environ.get("VGLB_LIB_PATH") or os.path.join(_HERE, "libvgl_b200.so")  # env override: developer A/B builds
 _LIB = None
 
 GEN_RMAT, GEN_KRONECKER, GEN_UNIFORM = 0, 1, 2

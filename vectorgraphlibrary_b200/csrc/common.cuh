@@ -72,8 +72,14 @@ struct vglb_graph
     float *d_pr_contrib[2];
     double *d_pr_dangling; // one slot per sweep
     int pr_dangling_slots;
-    int32_t *d_pr_chunk_row; // chunk table of the PageRank sweep (pagerank.cu)
-    int32_t pr_big_rows, pr_chunks;
+    void *d_pr_tasks;           // warp-task table of the PageRank sweep (pagerank.cu)
+    float *d_pr_piece_partial;  // partial sums of the pieces of long rows
+    int32_t *d_pr_piece_count;  // arrival counters of the long rows
+    int32_t pr_ntasks;
+    int32_t *d_pr_ve_adj;       // padded column-major copy of the rows with 1..31 edges (VectorExtension twin)
+    int64_t *d_pr_ve_ptr;
+    int32_t pr_ve_segments;
+    int32_t col_of_row0;        // column id of local row 0 (0 unless the graph is one rank's part of a partitioned graph)
     // BFS / SSSP / CC scratch
     uint32_t *d_visited, *d_front_bm[2];
     int32_t *d_queue[2];
@@ -158,6 +164,19 @@ __device__ __forceinline__ int ld_gather_s32(const int *p, uint64_t pol)
     int r;
     asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
     return r;
+}
+
+// gathered value that is unlikely to be re-used by this SM: do not let it push hot lines out of L1
+__device__ __forceinline__ float ld_gather_cold_f32(const float *p, uint64_t pol)
+{
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));
+    return r;
+}
+// streaming stores of per-vertex results (written once per sweep, read by the next kernel)
+__device__ __forceinline__ void st_stream_f32(float *p, float v)
+{
+    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
 __device__ __forceinline__ float warp_sum_f32(float v)

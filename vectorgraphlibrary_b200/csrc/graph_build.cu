@@ -178,7 +178,7 @@ static void graph_free_fields(vglb_graph *g)
 {
     cudaFree(g->d_out_ptr); cudaFree(g->d_out_adj); cudaFree(g->d_in_ptr); cudaFree(g->d_in_adj);
     cudaFree(g->d_fwd); cudaFree(g->d_bwd); cudaFree(g->d_edge_order);
-    cudaFree(g->d_pr_inv); cudaFree(g->d_pr_contrib[0]); cudaFree(g->d_pr_contrib[1]); cudaFree(g->d_pr_dangling); cudaFree(g->d_pr_chunk_row);
+    cudaFree(g->d_pr_inv); cudaFree(g->d_pr_contrib[0]); cudaFree(g->d_pr_contrib[1]); cudaFree(g->d_pr_dangling); cudaFree(g->d_pr_tasks); cudaFree(g->d_pr_piece_partial); cudaFree(g->d_pr_piece_count); cudaFree(g->d_pr_ve_adj); cudaFree(g->d_pr_ve_ptr);
     cudaFree(g->d_visited); cudaFree(g->d_front_bm[0]); cudaFree(g->d_front_bm[1]);
     cudaFree(g->d_queue[0]); cudaFree(g->d_queue[1]); cudaFree(g->d_scratch_i32);
 }

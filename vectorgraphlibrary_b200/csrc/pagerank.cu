@@ -8,214 +8,302 @@
 //
 // B200 design: ONE kernel per sweep, no atomics on the rank vector, no host sync inside the loop.
 //   * contrib[v] = r[v]*inv[v] is produced by the epilogue of the previous sweep, so the E-pass gathers one fp32 per
-//     edge (the product is the same fp32 multiply the reference does per edge, pr.hpp:112-115);
-//   * rows are degree-sorted, so the load-balancing tiers are contiguous id ranges decided by blockIdx alone
-//     (replaces the ve / vc / collective tiers of multicore/advance_all_active.hpp:7-229):
-//         degree >= 4096 : one CTA per row, int4 column-index loads, block reduction
-//         32..4095       : one warp per row, int4 column-index loads, shuffle reduction
-//         16..31, 8..15, 4..7, 2..3, <=1 : 16 / 8 / 4 / 2 / 1 lanes per row (no divergence: neighbours in id have
-//                          neighbouring degrees), rows of one warp are adjacent in the adjacency array => coalesced
-//   * column indices are streamed (ld.global.nc.L1::no_allocate.L2::evict_first), the gathered contribution vector
-//     is kept L2-resident (ld.global.nc.L2::evict_last): 64 MB at scale 24 fits the 126 MB L2;
-//   * the epilogue fuses post-op (:118-121), next sweep's contribution, and the NEXT sweep's dangling mass (summed in
-//     fp64: block reduction + one atomicAdd(double) per CTA), so `reduce` never returns to the host.
+//     edge (the product is the same fp32 multiply the reference does per edge, pr.hpp:112-115).
+//   * What bounds the sweep (profiles/r1_pr_gather_lab*.txt): not HBM but the SM's L1-miss request port — one 128-byte
+//     line request per clock per SM, whatever the number of useful bytes. Streaming the adjacency alone runs at
+//     6.9 TB/s; the same stream with one random 4-byte gather per edge runs at 0.69 ms per sweep with the request port
+//     95 % busy. Two things therefore decide the speed: (1) every SM must keep the request port full — many
+//     independent gathers in flight per warp, no dependent pointer chasing per row; (2) nothing but the gather target
+//     may live in L1 — shared memory is NOT used for staging (a 16 KB tile buffer per CTA costs 35 %, because the L1
+//     that holds the hubs' contributions shrinks), adjacency / inverse degrees / results bypass L1.
+//   * Load balance (replaces the ve / vc / collective tiers of multicore/advance_all_active.hpp:7-229). Rows are
+//     degree-sorted, so degree classes are contiguous id ranges:
+//       degree >= 32 ("heavy", 89 % of the edges of RMAT-24): the row range is cut into warp TASKS of consecutive rows
+//         (<= 31 rows, ~2048 edges; rows >= 4096 edges are cut into 4096-edge pieces). A warp streams its task's edge
+//         range FLAT — 128 consecutive column indices per step as coalesced int4 loads, two steps (256 gathers) in
+//         flight — and assigns the gathered values to rows with a shuffle-based segmented scan keyed by row; lane k
+//         owns row k of the task and pulls the row's step total with an indexed shuffle. No shared memory, no atomics,
+//         a fixed summation order. Pieces of a long row leave partial sums in a scratch array; the last piece to
+//         arrive (one atomic counter per long row) adds them in piece order and runs the row's epilogue.
+//       degree 16..31, 8..15, 4..7, 2..3, 1 : 16 / 8 / 4 / 2 / 1 lanes per row (neighbours in id have neighbouring
+//         degrees, so the rows of one warp are adjacent in the adjacency array => coalesced), two passes in flight.
+//       degree 0 (56 % of the rows): no row pointers, no gathers — only the post-op, coalesced.
+//   * Column indices are streamed (ld.global.nc.L1::no_allocate + L2 evict-first); the gathered contribution vector is
+//     kept L2-resident (evict-last; 64 MB at scale 24 fits the 126 MB L2) and only ids below PR_COLD_ID allocate in L1.
+//   * The epilogue fuses post-op (:118-121), next sweep's contribution, and the NEXT sweep's dangling mass (summed in
+//     fp64: block reduction + one atomicAdd(double) per CTA), so `reduce` never returns to the host. On a partitioned
+//     graph it also stores the contribution into every peer GPU's copy of the vector (NVLink P2P stores): the
+//     allgather of the reference's exchange_vertices_array (mpi_exchange.hpp:155-271) happens inside the sweep.
 // Row sums are fp32 trees instead of the reference's sequential fp32 (difference ~1e-7 relative, tolerance 1e-6).
 // HBM roofline: algorithmic bytes per sweep = 8E (index + gathered value per edge) + 16V (row pointer, inv read,
 // contribution write) [+4V rank write on the last sweep].
+#include <limits.h>
 #include <math.h>
 #include <stdlib.h>
 
+#include <vector>
+
+#include <cub/device/device_scan.cuh>
+
 #include "common.cuh"
+#include "pagerank.cuh"
 
-#define PR_THREADS 256
-#define PR_WARP_ROWS_PER_WARP 8   // rows handled by one warp of the warp tier
-#define PR_GROUP_PASSES 16        // passes of a CTA over its rows in the sub-warp tiers
-
-struct PrParams
+__device__ __forceinline__ float pr_gather(const PrParams &P, const L2Pol &pol, int32_t v)
 {
-    const int64_t *ptr;
-    const int32_t *adj;
-    const float *contrib_in;
-    const float *inv;
-    float *contrib_out;
-    float *rank_out; // written on the final sweep only (may be NULL otherwise)
-    const double *dangling_in;
-    double *dangling_out;
-    int32_t V;
-    float k, d, v_as_float;
-    int32_t tier_border[VGLB_NUM_TIERS]; // first row NOT in tier t
-    int32_t block_start[VGLB_NUM_TIERS]; // first block of tier t (tier 7 shares tier 6's kernel path)
-};
+    if (v >= PR_COLD_ID) return ld_gather_cold_f32(P.contrib_in + v, pol.keep);
+    return ld_gather_f32(P.contrib_in + v, pol.keep);
+}
 
-struct L2Pol
+__device__ __forceinline__ void pr_epilogue(const PrParams &P, const L2Pol &pol, int32_t row, float sum, float dang, double &dang_local)
 {
-    uint64_t stream, keep;
-};
-
-__device__ __forceinline__ void pr_epilogue(const PrParams &P, int32_t row, float sum, float dang, double &dang_local)
-{
-    const float inv_r = P.inv[row];
+    const float inv_r = ld_stream_f32(P.inv + row, pol.stream);
     // k + d * (rank + dangling) — pr.hpp:118-121, no FMA contraction (the x86-64 reference build has none)
     const float rank = __fadd_rn(P.k, __fmul_rn(P.d, __fadd_rn(sum, dang)));
-    P.contrib_out[row] = __fmul_rn(rank, inv_r);
-    if (P.rank_out) P.rank_out[row] = rank;
+    const float c = __fmul_rn(rank, inv_r);
+    st_stream_f32(P.contrib_out + row, c);
+    for (int p = 0; p < P.npeers; p++) st_stream_f32(P.peer_out[p] + row, c);
+    if (P.rank_out) st_stream_f32(P.rank_out + row, rank);
     if (inv_r == 0.0f) dang_local += (double)__fdiv_rn(rank, P.v_as_float); // pr.hpp:94-101
 }
 
-// sum over one row with `nthreads` cooperating threads (tid in [0,nthreads)), int4 body + scalar head/tail
-template <int NTHREADS>
-__device__ __forceinline__ float pr_row_partial(const PrParams &P, const L2Pol &pol, int32_t row, int64_t s, int64_t e, int tid)
+// ---- heavy region: one warp per task ---------------------------------------------------------------------------------
+
+// the four gathers of one lane's int4 at relative position p, split at the row boundary nb
+struct Quad
 {
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-    const int64_t s4 = (s + 3) & ~(int64_t)3;
-    const int64_t e4 = e & ~(int64_t)3;
-    if (s4 >= e4)
+    float left, right; // sums of the elements before / at-or-after the boundary
+};
+
+__device__ __forceinline__ Quad pr_quad(const PrParams &P, const L2Pol &pol, const int4 a, int p, int e_lo, int e_hi, int nb, int col_cur)
+{
+    // element j lives at relative position p + j; valid iff e_lo <= p + j < e_hi; its row's column id is col_cur (+1 past nb)
+    const int c[4] = {a.x, a.y, a.z, a.w};
+    float x[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
     {
-        for (int64_t p = s + tid; p < e; p += NTHREADS)
-        {
-            const int32_t v = ld_stream_s32(P.adj + p, pol.stream);
-            if (v != row) acc0 += ld_gather_f32(P.contrib_in + v, pol.keep);
-        }
-        return acc0;
+        const int q = p + j;
+        const int self = col_cur + (q >= nb ? 1 : 0);
+        x[j] = (q >= e_lo && q < e_hi && c[j] != self) ? pr_gather(P, pol, c[j]) : 0.f;
     }
-    // head (< 4 elements) and tail (< 4 elements)
-    if (s + tid < s4)
+    Quad r;
+    r.left = 0.f;
+    r.right = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
     {
-        const int32_t v = ld_stream_s32(P.adj + s + tid, pol.stream);
-        if (v != row) acc1 += ld_gather_f32(P.contrib_in + v, pol.keep);
+        if (p + j < nb) r.left += x[j];
+        else r.right += x[j];
     }
-    if (e4 + tid < e)
-    {
-        const int32_t v = ld_stream_s32(P.adj + e4 + tid, pol.stream);
-        if (v != row) acc2 += ld_gather_f32(P.contrib_in + v, pol.keep);
-    }
-    const int4 *adj4 = reinterpret_cast<const int4 *>(P.adj);
-    const int64_t q_end = e4 >> 2;
-    int64_t q = (s4 >> 2) + tid;
-    // two vectors (8 gathers) in flight per thread
-    for (; q + NTHREADS < q_end; q += 2 * NTHREADS)
-    {
-        const int4 a = ld_stream_v4(adj4 + q, pol.stream);
-        const int4 b = ld_stream_v4(adj4 + q + NTHREADS, pol.stream);
-        const float a0 = a.x != row ? ld_gather_f32(P.contrib_in + a.x, pol.keep) : 0.f;
-        const float a1 = a.y != row ? ld_gather_f32(P.contrib_in + a.y, pol.keep) : 0.f;
-        const float a2 = a.z != row ? ld_gather_f32(P.contrib_in + a.z, pol.keep) : 0.f;
-        const float a3 = a.w != row ? ld_gather_f32(P.contrib_in + a.w, pol.keep) : 0.f;
-        const float b0 = b.x != row ? ld_gather_f32(P.contrib_in + b.x, pol.keep) : 0.f;
-        const float b1 = b.y != row ? ld_gather_f32(P.contrib_in + b.y, pol.keep) : 0.f;
-        const float b2 = b.z != row ? ld_gather_f32(P.contrib_in + b.z, pol.keep) : 0.f;
-        const float b3 = b.w != row ? ld_gather_f32(P.contrib_in + b.w, pol.keep) : 0.f;
-        acc0 += a0 + b0;
-        acc1 += a1 + b1;
-        acc2 += a2 + b2;
-        acc3 += a3 + b3;
-    }
-    if (q < q_end)
-    {
-        const int4 a = ld_stream_v4(adj4 + q, pol.stream);
-        if (a.x != row) acc0 += ld_gather_f32(P.contrib_in + a.x, pol.keep);
-        if (a.y != row) acc1 += ld_gather_f32(P.contrib_in + a.y, pol.keep);
-        if (a.z != row) acc2 += ld_gather_f32(P.contrib_in + a.z, pol.keep);
-        if (a.w != row) acc3 += ld_gather_f32(P.contrib_in + a.w, pol.keep);
-    }
-    return (acc0 + acc1) + (acc2 + acc3);
+    return r;
 }
 
-// G lanes per row, rows [row0, row1) of this CTA
-template <int G>
-__device__ __forceinline__ void pr_group_tier(const PrParams &P, const L2Pol &pol, int32_t row0, int32_t row1, float dang, double &dang_local)
+__device__ __forceinline__ void pr_heavy_task(const PrParams &P, const L2Pol &pol, const PrTask T, int lane, float dang, double &dang_local)
 {
-    constexpr int GROUPS = PR_THREADS / G;
-    const int gid = threadIdx.x / G, gl = threadIdx.x % G;
-    for (int32_t base = row0; base < row1; base += GROUPS)
+    const unsigned FULL = 0xffffffffu;
+    const int64_t a4 = T.e0 & ~(int64_t)3;
+    const int e_lo = (int)(T.e0 - a4), e_hi = e_lo + T.e_len;
+    const int4 *adj4 = reinterpret_cast<const int4 *>(P.adj + a4);
+    const int nsteps = (e_hi + 127) >> 7;
+
+    if (T.nrows == 1)
     {
-        const int32_t row = base + gid;
-        float acc = 0.f;
-        if (row < row1)
+        // one row (or one piece of a long row): plain per-lane accumulation, four steps (512 gathers) in flight
+        const int self = P.col_of_row0 + T.row0;
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+        for (int s = 0; s < nsteps; s += 4)
         {
-            const int64_t s = P.ptr[row], e = P.ptr[row + 1];
-            // degree is in [G, 2G): at most two column indices per lane, both loads issued before the gathers
-            const int64_t p0 = s + gl, p1 = p0 + G;
-            int32_t v0 = row, v1 = row;
-            if (p0 < e) v0 = ld_stream_s32(P.adj + p0, pol.stream);
-            if (p1 < e) v1 = ld_stream_s32(P.adj + p1, pol.stream);
-            if (v0 != row) acc += ld_gather_f32(P.contrib_in + v0, pol.keep);
-            if (v1 != row) acc += ld_gather_f32(P.contrib_in + v1, pol.keep);
-            for (int64_t p = p1 + G; p < e; p += G) // only when a caller passes rows with degree >= 2G
+            int4 a[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
             {
-                const int32_t v = ld_stream_s32(P.adj + p, pol.stream);
-                if (v != row) acc += ld_gather_f32(P.contrib_in + v, pol.keep);
+                const int p = (s + u) * 128 + lane * 4;
+                a[u] = p < e_hi ? ld_stream_v4(adj4 + (s + u) * 32 + lane, pol.stream) : make_int4(self, self, self, self);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+            {
+                const int p = (s + u) * 128 + lane * 4;
+                const float x0 = (p + 0 >= e_lo && p + 0 < e_hi && a[u].x != self) ? pr_gather(P, pol, a[u].x) : 0.f;
+                const float x1 = (p + 1 >= e_lo && p + 1 < e_hi && a[u].y != self) ? pr_gather(P, pol, a[u].y) : 0.f;
+                const float x2 = (p + 2 >= e_lo && p + 2 < e_hi && a[u].z != self) ? pr_gather(P, pol, a[u].z) : 0.f;
+                const float x3 = (p + 3 >= e_lo && p + 3 < e_hi && a[u].w != self) ? pr_gather(P, pol, a[u].w) : 0.f;
+                acc0 += x0;
+                acc1 += x1;
+                acc2 += x2;
+                acc3 += x3;
             }
         }
+        const float acc = warp_sum_f32((acc0 + acc1) + (acc2 + acc3));
+        if (T.slot < 0)
+        {
+            if (lane == 0) pr_epilogue(P, pol, T.row0, acc, dang, dang_local);
+            return;
+        }
+        // piece of a long row: leave the partial sum; the last piece to arrive finishes the row
+        int last = 0;
+        if (lane == 0)
+        {
+            __stcg(P.piece_partial + T.slot, acc);
+            __threadfence();
+            last = atomicAdd(P.piece_count + T.row0, 1) == T.npieces - 1;
+        }
+        last = __shfl_sync(FULL, last, 0);
+        if (!last) return;
+        __threadfence();
+        float t = 0.f;
+        for (int i = lane; i < T.npieces; i += 32) t += __ldcg(P.piece_partial + T.slot_first + i);
+        t = warp_sum_f32(t);
+        if (lane == 0)
+        {
+            P.piece_count[T.row0] = 0; // ready for the next sweep
+            pr_epilogue(P, pol, T.row0, t, dang, dang_local);
+        }
+        return;
+    }
+
+    // 2..31 rows, each >= 32 edges. Lane k <= nrows holds the relative boundary b_k = ptr[row0 + k] - a4.
+    int bk = INT_MAX;
+    if (lane <= T.nrows) bk = (int)(P.ptr[T.row0 + lane] - a4);
+    int bk1 = __shfl_down_sync(FULL, bk, 1);
+    if (lane == 31) bk1 = INT_MAX;
+    // a lane's first element moves 128 positions per step; rows are >= minlen long, so its row index advances by at
+    // most ceil(128 / minlen) per step
+    const int minlen = __shfl_sync(FULL, bk, T.nrows) - __shfl_sync(FULL, bk, T.nrows - 1);
+    const int rounds = min(4, 127 / max(minlen, 32) + 1);
+    float acc = 0.f; // row `lane` of the task
+    int cur = 0;     // row (within the task) of this lane's first element of the current step
+    for (int s = 0; s < nsteps; s += 2)
+    {
+        int4 a[2];
+        int nb[2], curs[2];
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (gl == 0 && row < row1) pr_epilogue(P, row, acc, dang, dang_local);
+        for (int u = 0; u < 2; u++)
+        {
+            const int p = (s + u) * 128 + lane * 4;
+            for (int r = 0; r < rounds; r++)
+            {
+                const int b = __shfl_sync(FULL, bk, min(cur + 1, 31));
+                if (cur < T.nrows && b <= p) cur++;
+            }
+            curs[u] = cur;
+            nb[u] = __shfl_sync(FULL, bk, min(cur + 1, 31));
+            if (cur >= T.nrows) nb[u] = INT_MAX;
+            a[u] = p < e_hi ? ld_stream_v4(adj4 + (s + u) * 32 + lane, pol.stream) : make_int4(0, 0, 0, 0);
+        }
+        Quad qd[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++)
+        {
+            const int p = (s + u) * 128 + lane * 4;
+            qd[u] = pr_quad(P, pol, a[u], p, e_lo, e_hi, nb[u], P.col_of_row0 + T.row0 + curs[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++)
+        {
+            const int sb = (s + u) * 128, p = sb + lane * 4;
+            const bool inside = nb[u] <= p + 3; // a row ends inside this lane's four elements
+            const int key = curs[u] + (inside ? 1 : 0);
+            float y = inside ? qd[u].right : qd[u].left;
+            // inclusive segmented scan of y keyed by the row of the lane's last element (keys are non-decreasing)
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const float yu = __shfl_up_sync(FULL, y, o);
+                const int ku = __shfl_up_sync(FULL, key, o);
+                if (lane >= o && ku == key) y += yu;
+            }
+            // lane k owns row k: its elements of this step end in lane lb; pull the row's step total
+            const int lo = max(bk, sb), hi = min(bk1, sb + 128);
+            const bool active = lane < T.nrows && lo < hi;
+            const int lb = active ? ((hi - 1 - sb) >> 2) : 0;
+            const bool through = bk1 > sb + 4 * lb + 3; // row runs through lane lb's last element (or ends exactly there)
+            const int src = through ? lb : max(lb - 1, 0);
+            const float yv = __shfl_sync(FULL, y, src);
+            const int kv = __shfl_sync(FULL, key, src);
+            const float lv = __shfl_sync(FULL, qd[u].left, lb);
+            if (active)
+            {
+                float t = (kv == lane && (through || lb >= 1)) ? yv : 0.f;
+                if (!through) t += lv;
+                acc += t;
+            }
+        }
+    }
+    if (lane < T.nrows) pr_epilogue(P, pol, T.row0 + lane, acc, dang, dang_local);
+}
+
+// ---- tail: rows with 1..31 edges, lane per row over the padded column-major copy -----------------------------------
+// (the reference's VectorExtension, vgl_datastructures/graphs/undirected_containers/vect_csr/vector_extension/
+//  vector_extension.hpp:45-106: segments of 32 consecutive rows, padded to the segment's longest row with the row's own
+//  id; rows are degree-sorted, so the padding is a few per cent). No row pointers, no shuffles, every load coalesced and
+//  independent; two segments are in flight per warp.
+__device__ __forceinline__ void pr_tail_segments(const PrParams &P, const L2Pol &pol, int seg0, int seg1, int lane, float dang, double &dang_local)
+{
+    for (int seg = seg0; seg < seg1; seg += 2)
+    {
+        const bool two = seg + 1 < seg1;
+        const int64_t b0 = P.ve_ptr[seg], b1 = P.ve_ptr[seg + 1], b2 = two ? P.ve_ptr[seg + 2] : b1;
+        const int d0 = (int)((b1 - b0) >> 5), d1 = (int)((b2 - b1) >> 5);
+        const int32_t row_a = P.tail_first + seg * 32 + lane, row_b = row_a + 32;
+        const int32_t self_a = P.col_of_row0 + row_a, self_b = P.col_of_row0 + row_b;
+        const int32_t *pa = P.ve_adj + b0 + lane, *pb = P.ve_adj + b1 + lane;
+        float acc_a = 0.f, acc_b = 0.f;
+        const int dmax = max(d0, d1);
+        for (int j = 0; j < dmax; j += 2)
+        {
+            const int32_t a0 = j < d0 ? ld_stream_s32(pa + j * 32, pol.stream) : self_a;
+            const int32_t a1 = j + 1 < d0 ? ld_stream_s32(pa + (j + 1) * 32, pol.stream) : self_a;
+            const int32_t c0 = j < d1 ? ld_stream_s32(pb + j * 32, pol.stream) : self_b;
+            const int32_t c1 = j + 1 < d1 ? ld_stream_s32(pb + (j + 1) * 32, pol.stream) : self_b;
+            const float x0 = a0 != self_a ? pr_gather(P, pol, a0) : 0.f;
+            const float x1 = a1 != self_a ? pr_gather(P, pol, a1) : 0.f;
+            const float y0 = c0 != self_b ? pr_gather(P, pol, c0) : 0.f;
+            const float y1 = c1 != self_b ? pr_gather(P, pol, c1) : 0.f;
+            acc_a += x0 + x1;
+            acc_b += y0 + y1;
+        }
+        if (row_a < P.zero_first) pr_epilogue(P, pol, row_a, acc_a, dang, dang_local);
+        if (two && row_b < P.zero_first) pr_epilogue(P, pol, row_b, acc_b, dang, dang_local);
     }
 }
 
-__global__ void __launch_bounds__(PR_THREADS) pr_sweep_kernel(const __grid_constant__ PrParams P)
+__global__ void __launch_bounds__(PR_THREADS, PR_MIN_CTAS) pr_sweep_kernel(const __grid_constant__ PrParams P)
 {
     L2Pol pol;
     pol.stream = l2_policy_evict_first();
     pol.keep = l2_policy_evict_last();
-    __shared__ float s_part[PR_THREADS / 32];
-    __shared__ double s_dang[PR_THREADS / 32];
-    const int b = blockIdx.x;
+    __shared__ double s_dang[PR_WARPS];
+    int b = blockIdx.x;
+    if (P.interleave)
+    {
+        // the tail tiers are latency-bound, the heavy region is throughput-bound: mix their blocks so that both kinds
+        // are resident on every SM at any time. Block m is a tail block whenever floor((m+1)*ntail/M) advances.
+        const long long ntail = (long long)gridDim.x - P.heavy_blocks, M = gridDim.x, m = b;
+        const long long tails_before = m * ntail / M, tails_after = (m + 1) * ntail / M;
+        b = tails_after > tails_before ? (int)(P.heavy_blocks + tails_before) : (int)(m - tails_before);
+    }
     const float dang = (float)(*P.dangling_in);
     double dang_local = 0.0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    if (b < P.block_start[1])
+    if (b < P.heavy_blocks)
     {
-        // tier 0: one CTA per row
-        const int32_t row = b;
-        const int64_t s = P.ptr[row], e = P.ptr[row + 1];
-        float acc = pr_row_partial<PR_THREADS>(P, pol, row, s, e, threadIdx.x);
-        acc = warp_sum_f32(acc);
-        if (lane == 0) s_part[warp] = acc;
-        __syncthreads();
-        if (threadIdx.x == 0)
-        {
-            float t = 0.f;
-#pragma unroll
-            for (int w = 0; w < PR_THREADS / 32; w++) t += s_part[w];
-            pr_epilogue(P, row, t, dang, dang_local);
-        }
+        const int t = b * PR_WARPS + warp;
+        if (t < P.ntasks) pr_heavy_task(P, pol, P.tasks[t], lane, dang, dang_local);
     }
-    else if (b < P.block_start[2])
+    else if (b < P.heavy_blocks + P.tail_blocks)
     {
-        // tier 1: one warp per row, PR_WARP_ROWS_PER_WARP rows per warp
-        constexpr int ROWS = (PR_THREADS / 32) * PR_WARP_ROWS_PER_WARP;
-        const int32_t row0 = P.tier_border[0] + (b - P.block_start[1]) * ROWS;
-        const int32_t row1 = min(row0 + ROWS, P.tier_border[1]);
-        for (int32_t row = row0 + warp; row < row1; row += PR_THREADS / 32)
-        {
-            const int64_t s = P.ptr[row], e = P.ptr[row + 1];
-            float acc = pr_row_partial<32>(P, pol, row, s, e, lane);
-            acc = warp_sum_f32(acc);
-            if (lane == 0) pr_epilogue(P, row, acc, dang, dang_local);
-        }
+        const int seg0 = ((b - P.heavy_blocks) * PR_WARPS + warp) * PR_VE_SEGS_PER_WARP;
+        pr_tail_segments(P, pol, seg0, min(seg0 + PR_VE_SEGS_PER_WARP, P.ve_segments), lane, dang, dang_local);
     }
     else
     {
-        int t = 2;
-#pragma unroll
-        for (int i = 3; i < VGLB_NUM_TIERS - 1; i++)
-            if (b >= P.block_start[i]) t = i;
-        const int32_t tier_first = P.tier_border[t - 1];
-        const int32_t tier_last = (t == VGLB_NUM_TIERS - 2) ? P.V : P.tier_border[t];
-        const int G = 32 >> (t - 1); // t=2:16, 3:8, 4:4, 5:2, 6:1
-        const int32_t rows_per_cta = (PR_THREADS / G) * PR_GROUP_PASSES;
-        const int32_t row0 = tier_first + (b - P.block_start[t]) * rows_per_cta;
-        const int32_t row1 = min(row0 + rows_per_cta, tier_last);
-        switch (t)
-        {
-        case 2: pr_group_tier<16>(P, pol, row0, row1, dang, dang_local); break;
-        case 3: pr_group_tier<8>(P, pol, row0, row1, dang, dang_local); break;
-        case 4: pr_group_tier<4>(P, pol, row0, row1, dang, dang_local); break;
-        case 5: pr_group_tier<2>(P, pol, row0, row1, dang, dang_local); break;
-        default: pr_group_tier<1>(P, pol, row0, row1, dang, dang_local); break;
-        }
+        // rows without out-edges: only the post-op, coalesced
+        const int32_t row0 = P.zero_first + (b - P.heavy_blocks - P.tail_blocks) * PR_ZERO_ROWS_PER_CTA;
+        const int32_t row1 = min(row0 + PR_ZERO_ROWS_PER_CTA, P.rows);
+#pragma unroll 4
+        for (int32_t row = row0 + threadIdx.x; row < row1; row += PR_THREADS) pr_epilogue(P, pol, row, 0.f, dang, dang_local);
     }
     // next sweep's dangling mass: fp64 block reduction, one atomic per CTA that has any
     dang_local = warp_sum_f64(dang_local);
@@ -225,7 +313,7 @@ __global__ void __launch_bounds__(PR_THREADS) pr_sweep_kernel(const __grid_const
     {
         double t = 0.0;
 #pragma unroll
-        for (int w = 0; w < PR_THREADS / 32; w++) t += s_dang[w];
+        for (int w = 0; w < PR_WARPS; w++) t += s_dang[w];
         if (t != 0.0) atomicAdd(P.dangling_out, t);
     }
 }
@@ -245,7 +333,7 @@ __global__ void pr_inverse_degree_kernel(const int32_t *__restrict__ indeg, int3
 __global__ void pr_init_kernel(const float *__restrict__ inv, int32_t V, float r0, float v_as_float,
                                float *__restrict__ contrib, double *__restrict__ dangling0)
 {
-    __shared__ double s_dang[PR_THREADS / 32];
+    __shared__ double s_dang[PR_WARPS];
     double local = 0.0;
     for (int32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x)
     {
@@ -259,7 +347,7 @@ __global__ void pr_init_kernel(const float *__restrict__ inv, int32_t V, float r
     if (threadIdx.x == 0)
     {
         double t = 0.0;
-        for (int w = 0; w < PR_THREADS / 32; w++) t += s_dang[w];
+        for (int w = 0; w < PR_WARPS; w++) t += s_dang[w];
         if (t != 0.0) atomicAdd(dangling0, t);
     }
 }
@@ -270,7 +358,142 @@ __global__ void pr_fill_kernel(float *a, int32_t n, float val)
     if (i < n) a[i] = val;
 }
 
-static int pr_prepare(vglb_ctx *ctx, vglb_graph *g, int iters)
+// Warp tasks of the heavy region (rows with degree >= 32), built once per graph on the host from the row pointers of
+// that region (a few MB): consecutive rows are packed until ~PR_TASK_EDGES edges or PR_TASK_MAX_ROWS rows; rows with
+// >= PR_PIECE_EDGES edges are cut into pieces.
+static int pr_build_tasks(vglb_ctx *ctx, vglb_graph *g)
+{
+    const int32_t heavy_rows = g->tier_border[1];
+    std::vector<int64_t> ptr((size_t)heavy_rows + 1);
+    if (heavy_rows > 0)
+    {
+        CUDA_TRY(cudaMemcpyAsync(ptr.data(), g->d_out_ptr, ((size_t)heavy_rows + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    std::vector<PrTask> tasks;
+    int32_t slots = 0;
+    int32_t r = 0;
+    while (r < heavy_rows)
+    {
+        const int64_t d = ptr[r + 1] - ptr[r];
+        if (d >= PR_PIECE_EDGES)
+        {
+            const int32_t np = (int32_t)((d + PR_PIECE_EDGES - 1) / PR_PIECE_EDGES);
+            for (int32_t i = 0; i < np; i++)
+            {
+                PrTask t;
+                t.e0 = ptr[r] + (int64_t)i * PR_PIECE_EDGES;
+                t.e_len = (int32_t)((i == np - 1) ? d - (int64_t)i * PR_PIECE_EDGES : PR_PIECE_EDGES);
+                t.row0 = r;
+                t.nrows = 1;
+                t.slot = slots + i;
+                t.slot_first = slots;
+                t.npieces = np;
+                tasks.push_back(t);
+            }
+            slots += np;
+            r++;
+            continue;
+        }
+        PrTask t;
+        t.e0 = ptr[r];
+        t.row0 = r;
+        t.nrows = 0;
+        t.slot = -1;
+        t.slot_first = 0;
+        t.npieces = 0;
+        int64_t edges = 0;
+        while (r < heavy_rows && t.nrows < PR_TASK_MAX_ROWS)
+        {
+            const int64_t dr = ptr[r + 1] - ptr[r];
+            if (dr >= PR_PIECE_EDGES) break;
+            if (t.nrows > 0 && edges + dr > PR_TASK_EDGES + PR_TASK_EDGES / 2) break;
+            edges += dr;
+            t.nrows++;
+            r++;
+            if (edges >= PR_TASK_EDGES) break;
+        }
+        t.e_len = (int32_t)edges;
+        tasks.push_back(t);
+    }
+    g->pr_ntasks = (int32_t)tasks.size();
+    if (!tasks.empty())
+    {
+        CUDA_TRY(cudaMalloc(&g->d_pr_tasks, tasks.size() * sizeof(PrTask)));
+        CUDA_TRY(cudaMemcpyAsync(g->d_pr_tasks, tasks.data(), tasks.size() * sizeof(PrTask), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CUDA_TRY(cudaMalloc(&g->d_pr_piece_partial, (size_t)(slots > 0 ? slots : 1) * 4));
+    const size_t counters = (size_t)(g->tier_border[0] > 0 ? g->tier_border[0] : 1);
+    CUDA_TRY(cudaMalloc(&g->d_pr_piece_count, counters * 4));
+    CUDA_TRY(cudaMemsetAsync(g->d_pr_piece_count, 0, counters * 4, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return VGLB_OK;
+}
+
+// ---- padded column-major copy of the tail rows (built once per graph) -------------------------------------------------
+__global__ void pr_ve_seglen_kernel(const int64_t *__restrict__ ptr, int32_t tail_first, int32_t segments, int64_t *__restrict__ seglen)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < segments)
+    {
+        const int32_t r = tail_first + s * 32; // the first row of a segment is its longest (rows are degree-sorted)
+        seglen[s] = 32 * (ptr[r + 1] - ptr[r]);
+    }
+    if (s == segments) seglen[s] = 0;
+}
+
+__global__ void pr_ve_fill_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, int32_t tail_first,
+                                  int32_t zero_first, int32_t col_of_row0, int32_t segments,
+                                  const int64_t *__restrict__ ve_ptr, int32_t *__restrict__ ve_adj)
+{
+    const int lane = threadIdx.x & 31;
+    const int seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (seg >= segments) return;
+    const int32_t row = tail_first + seg * 32 + lane;
+    int64_t s = 0;
+    int d = 0;
+    if (row < zero_first)
+    {
+        s = ptr[row];
+        d = (int)(ptr[row + 1] - s);
+    }
+    const int64_t base = ve_ptr[seg];
+    const int maxd = (int)((ve_ptr[seg + 1] - base) >> 5);
+    for (int j = 0; j < maxd; j++) ve_adj[base + j * 32 + lane] = j < d ? adj[s + j] : col_of_row0 + row;
+}
+
+static int pr_build_tail_copy(vglb_ctx *ctx, vglb_graph *g)
+{
+    const int32_t tail_first = g->tier_border[1], zero_first = g->tier_border[VGLB_NUM_TIERS - 2];
+    const int32_t segments = (int32_t)ceil_div64(zero_first - tail_first, 32);
+    g->pr_ve_segments = segments;
+    CUDA_TRY(cudaMalloc(&g->d_pr_ve_ptr, ((size_t)segments + 2) * 8));
+    int64_t *d_len = NULL;
+    CUDA_TRY(cudaMalloc(&d_len, ((size_t)segments + 2) * 8));
+    pr_ve_seglen_kernel<<<(unsigned)ceil_div64(segments + 1, 256), 256, 0, ctx->stream>>>(g->d_out_ptr, tail_first, segments, d_len);
+    KERNEL_TRY();
+    size_t tmp_bytes = 0;
+    void *tmp = NULL;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(NULL, tmp_bytes, d_len, g->d_pr_ve_ptr, segments + 1, ctx->stream));
+    CUDA_TRY(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_len, g->d_pr_ve_ptr, segments + 1, ctx->stream));
+    int64_t total = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, g->d_pr_ve_ptr + segments, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    cudaFree(tmp);
+    cudaFree(d_len);
+    CUDA_TRY(cudaMalloc(&g->d_pr_ve_adj, (size_t)(total > 0 ? total : 1) * 4));
+    if (segments > 0)
+    {
+        pr_ve_fill_kernel<<<(unsigned)ceil_div64((int64_t)segments * 32, 256), 256, 0, ctx->stream>>>(
+            g->d_out_ptr, g->d_out_adj, tail_first, zero_first, g->col_of_row0, segments, g->d_pr_ve_ptr, g->d_pr_ve_adj);
+        KERNEL_TRY();
+    }
+    ctx->launches += 2;
+    return VGLB_OK;
+}
+
+int vglb_pr_prepare(vglb_ctx *ctx, vglb_graph *g, int iters)
 {
     if (!g->d_pr_inv)
     {
@@ -287,6 +510,13 @@ static int pr_prepare(vglb_ctx *ctx, vglb_graph *g, int iters)
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         cudaFree(d_indeg);
     }
+    if (!g->d_pr_piece_count)
+    {
+        int rc = pr_build_tasks(ctx, g);
+        if (rc != VGLB_OK) return rc;
+        rc = pr_build_tail_copy(ctx, g);
+        if (rc != VGLB_OK) return rc;
+    }
     if (g->pr_dangling_slots < iters + 1)
     {
         cudaFree(g->d_pr_dangling);
@@ -297,41 +527,73 @@ static int pr_prepare(vglb_ctx *ctx, vglb_graph *g, int iters)
     return VGLB_OK;
 }
 
+// grid layout of one sweep over `rows` local rows: heavy blocks first, then the tail tiers
+int64_t vglb_pr_plan(const vglb_graph *g, int32_t rows, PrParams *P)
+{
+    P->ptr = g->d_out_ptr;
+    P->adj = g->d_out_adj;
+    P->rows = rows;
+    P->tasks = (const PrTask *)g->d_pr_tasks;
+    P->ntasks = g->pr_ntasks;
+    P->piece_partial = g->d_pr_piece_partial;
+    P->piece_count = g->d_pr_piece_count;
+    P->heavy_blocks = (int32_t)ceil_div64(g->pr_ntasks, PR_WARPS);
+    P->ve_adj = g->d_pr_ve_adj;
+    P->ve_ptr = g->d_pr_ve_ptr;
+    P->ve_segments = g->pr_ve_segments;
+    P->tail_first = g->tier_border[1];
+    P->zero_first = g->tier_border[VGLB_NUM_TIERS - 2];
+    P->tail_blocks = (int32_t)ceil_div64(g->pr_ve_segments, PR_WARPS * PR_VE_SEGS_PER_WARP);
+    int64_t nblocks = (int64_t)P->heavy_blocks + P->tail_blocks + ceil_div64(rows - P->zero_first, PR_ZERO_ROWS_PER_CTA);
+    // developer knob for timing experiments (results are wrong when set): 1 = heavy region only, 2 = tail tiers only
+    if (const char *m = getenv("VGLB_PR_ONLY"))
+    {
+        if (atoi(m) == 1) nblocks = P->heavy_blocks;
+        if (atoi(m) == 2) P->ntasks = 0;
+        if (atoi(m) == 3) { P->ntasks = 0; P->ve_segments = 0; }
+    }
+    P->interleave = 1;
+    if (const char *m = getenv("VGLB_PR_INTERLEAVE")) P->interleave = atoi(m);
+    if (getenv("VGLB_PR_ONLY")) P->interleave = 0;
+    return nblocks;
+}
+
+int vglb_pr_launch_sweep(vglb_ctx *ctx, const PrParams &P, int64_t nblocks)
+{
+    if (nblocks <= 0) return VGLB_OK;
+    // every KB of L1 holds hub contributions: ask for the smallest shared-memory carve-out (64 B static are used)
+    static bool carveout_set = false;
+    if (!carveout_set)
+    {
+        CUDA_TRY(cudaFuncSetAttribute(pr_sweep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
+        carveout_set = true;
+    }
+    pr_sweep_kernel<<<(unsigned)nblocks, PR_THREADS, 0, ctx->stream>>>(P);
+    KERNEL_TRY();
+    ctx->launches++;
+    return VGLB_OK;
+}
+
 extern "C" int vglb_pagerank(vglb_ctx *ctx, vglb_graph *g, int iters, float damping, float *d_ranks, vglb_stats *stats)
 {
     VGLB_REQUIRE(ctx != NULL && g != NULL && d_ranks != NULL, "vglb_pagerank: NULL argument");
     VGLB_REQUIRE(iters >= 0 && iters < (1 << 20), "vglb_pagerank: bad iteration count");
     CUDA_TRY(cudaSetDevice(ctx->device));
     const int64_t launches0 = ctx->launches;
-    int rc = pr_prepare(ctx, g, iters);
+    int rc = vglb_pr_prepare(ctx, g, iters);
     if (rc != VGLB_OK) return rc;
 
     const int32_t V = g->V;
     PrParams P;
-    P.ptr = g->d_out_ptr;
-    P.adj = g->d_out_adj;
+    memset(&P, 0, sizeof(P));
+    const int64_t nblocks = vglb_pr_plan(g, V, &P);
+    VGLB_REQUIRE(nblocks < 0x7fffffffLL, "vglb_pagerank: grid too large");
     P.inv = g->d_pr_inv;
-    P.V = V;
+    P.col_of_row0 = 0;
+    P.npeers = 0;
     P.d = damping;
     P.k = (float)((1.0 - (double)damping) / (double)((float)V)); // pr.hpp:37-38
     P.v_as_float = (float)V;
-    // block ranges per tier
-    int64_t nblocks = 0;
-    for (int t = 0; t < VGLB_NUM_TIERS; t++) P.tier_border[t] = g->tier_border[t];
-    for (int t = 0; t < VGLB_NUM_TIERS - 1; t++)
-    {
-        P.block_start[t] = (int32_t)nblocks;
-        const int32_t first = t == 0 ? 0 : g->tier_border[t - 1];
-        const int32_t last = (t == VGLB_NUM_TIERS - 2) ? V : g->tier_border[t]; // tier 6 also takes degree-0 rows
-        const int64_t rows = last - first;
-        int64_t rows_per_cta;
-        if (t == 0) rows_per_cta = 1;
-        else if (t == 1) rows_per_cta = (PR_THREADS / 32) * PR_WARP_ROWS_PER_WARP;
-        else rows_per_cta = (int64_t)(PR_THREADS / (32 >> (t - 1))) * PR_GROUP_PASSES;
-        nblocks += ceil_div64(rows, rows_per_cta);
-    }
-    P.block_start[VGLB_NUM_TIERS - 1] = (int32_t)nblocks;
-    VGLB_REQUIRE(nblocks < 0x7fffffffLL, "vglb_pagerank: grid too large");
 
     CUDA_TRY(cudaEventRecord(ctx->ev_start, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(g->d_pr_dangling, 0, (size_t)(iters + 1) * sizeof(double), ctx->stream));
@@ -356,9 +618,8 @@ extern "C" int vglb_pagerank(vglb_ctx *ctx, vglb_graph *g, int iters, float damp
         P.rank_out = (it == iters - 1) ? d_ranks : NULL;
         P.dangling_in = g->d_pr_dangling + it;
         P.dangling_out = g->d_pr_dangling + it + 1;
-        pr_sweep_kernel<<<(unsigned)nblocks, PR_THREADS, 0, ctx->stream>>>(P);
-        KERNEL_TRY();
-        ctx->launches++;
+        rc = vglb_pr_launch_sweep(ctx, P, nblocks);
+        if (rc != VGLB_OK) return rc;
     }
     CUDA_TRY(cudaEventRecord(ctx->ev_stop, ctx->stream));
     CUDA_TRY(cudaEventSynchronize(ctx->ev_stop));
