@@ -112,6 +112,14 @@ typedef struct vglb_graph_info
     const int32_t *d_orig_to_sorted; /* forward_conversion */
     const int32_t *d_sorted_to_orig; /* backward_conversion */
     const int64_t *d_edge_order;     /* edges_reorder_indexes or NULL */
+    /* 1D partition (see "multi-GPU" below); on one GPU: rank 0 of 1, columns = vertices_global = vertices */
+    int32_t part_rank, part_world;
+    int32_t rows_per_rank;           /* slice stride: column id = owner * rows_per_rank + local row */
+    int32_t col_of_row0;             /* part_rank * rows_per_rank */
+    int32_t vertices_global;         /* vertices of the whole graph (`vertices` = this rank's rows) */
+    int32_t reserved;
+    int64_t columns;                 /* length of a replicated vertex array = part_world * rows_per_rank */
+    int64_t edges_global;            /* edges of the whole graph (`edges` = this rank's) */
 } vglb_graph_info;
 int vglb_graph_get_info(vglb_graph *g, vglb_graph_info *info);
 /* threshold vertex for an arbitrary degree threshold (estimate_thresholds twin) */
@@ -199,6 +207,54 @@ int vglb_gnf_ne_u32(vglb_ctx *ctx, vglb_frontier *f, const uint32_t *d_a, const 
 int vglb_reduce_sum_i32(vglb_ctx *ctx, vglb_frontier *f, const int32_t *d_values, int64_t *out);
 int vglb_reduce_sum_f32(vglb_ctx *ctx, vglb_frontier *f, const float *d_values, double *out);
 int vglb_reduce_max_i32(vglb_ctx *ctx, vglb_frontier *f, const int32_t *d_values, int32_t *out);
+
+/* ---- multi-GPU: one process per GPU, 1D vertex partition, NCCL over NVLink ----------------------------------------
+ * Reference: the MPI layer of the NEC backend — vgl_mpi_init (vgl_runtime/helpers/library_data/init.hpp:5-38), the
+ * per-rank vertex ranges (vect_csr/mpi_api.hpp:6-26, get_api.hpp:66-94) and exchange_vertices_array
+ * (vgl_compute_api/common/mpi_exchange.hpp:155-271). Here the GRAPH is partitioned too (the reference replicates it):
+ * the degree-sorted ids s = 0..V-1 are dealt round-robin, owner(s) = s mod P, local row = s div P, so every rank owns
+ * a degree-sorted slice with ~V/P rows and ~E/P edges (hubs are spread over all ranks). Vertex state is replicated
+ * and indexed by COLUMN id = owner * rows_per_rank + local row; each rank computes the slice it owns and the slices
+ * are exchanged once per iteration (allgather of owned slices for PageRank contributions / BFS frontier bitmaps,
+ * all-to-all OR of candidate bitmaps for top-down BFS, allreduce(min) for SSSP distances / CC labels, allreduce of
+ * the convergence counters). vglb_pagerank / vglb_bfs / vglb_sssp / vglb_cc accept a partitioned graph: vertex
+ * outputs then hold THIS RANK's rows (info.vertices entries), `source_sorted` is a column id, and every rank must
+ * make the same call (they are collectives). */
+typedef struct vglb_comm vglb_comm;
+#define VGLB_UNIQUE_ID_BYTES 128
+int vglb_comm_unique_id(void *out_id /* VGLB_UNIQUE_ID_BYTES */);
+int vglb_comm_init(vglb_ctx *ctx, int rank, int world, const void *unique_id, vglb_comm **out);
+/* carries (rank, world) only — builds / inspects any rank's part in one process; collectives on it fail (VGLB_ENCCL) */
+int vglb_comm_init_detached(vglb_ctx *ctx, int rank, int world, vglb_comm **out);
+int vglb_comm_destroy(vglb_comm *comm);
+int vglb_comm_barrier(vglb_comm *comm);
+/* exchange_vertices_array: in-place allgather of equal slices of a device array (slice r at offset r*bytes_per_rank) */
+int vglb_comm_allgather(vglb_comm *comm, void *d_buf, size_t bytes_per_rank);
+int vglb_comm_allreduce_sum_i64(vglb_comm *comm, int64_t *d_buf, int count);
+int vglb_comm_allreduce_max_f64(vglb_comm *comm, double *h_value); /* host scalar, e.g. max-over-ranks timings */
+
+/* Build THIS RANK's part of the graph. Every rank passes the same edge list (host or device pointers) or the same
+ * generator arguments; edges are streamed in chunks twice (degree pass, then a pass that keeps the owned rows), so
+ * device memory is O(E/P + V) and E may exceed 2^31. symmetrize != 0 appends the reversed copy of every edge (CC).
+ * flags: VGLB_GRAPH_WITH_INCOMING. Rows list their neighbours hubs-first. */
+int vglb_graph_from_edges_partitioned(vglb_ctx *ctx, vglb_comm *comm, int32_t vertices, int64_t edges,
+                                      const int32_t *src, const int32_t *dst, int src_on_device, int symmetrize,
+                                      int flags, vglb_graph **out_graph);
+int vglb_graph_from_generator_partitioned(vglb_ctx *ctx, vglb_comm *comm, int kind, int scale, int64_t edges,
+                                          uint64_t seed, int a, int b, int c, int symmetrize, int flags,
+                                          vglb_graph **out_graph);
+/* VGL_Graph::move_to_device for one rank's part: host arrays of an already-built part (row pointers of this rank's
+ * `rows` rows, adjacency in column ids, ORIGINAL -> column map of the whole graph) copied to HBM. A collective when
+ * the communicator is live (edge totals are allreduced). */
+int vglb_graph_from_csr_partitioned(vglb_ctx *ctx, vglb_comm *comm, int32_t vertices_global, int32_t rows,
+                                    const int64_t *h_out_ptr, const int32_t *h_out_adj, const int32_t *h_orig_to_col,
+                                    const int64_t *h_in_ptr, const int32_t *h_in_adj, vglb_graph **out_graph);
+/* PageRank exchange on a partitioned graph: 0 = ncclAllGather after every sweep; 1 = the sweep's epilogue stores each
+ * contribution straight into every peer's copy of the vector over NVLink (CUDA IPC peer memory), and the dangling-mass
+ * allreduce doubles as the inter-sweep barrier. */
+#define VGLB_EXCHANGE_NCCL 0
+#define VGLB_EXCHANGE_P2P 1
+int vglb_graph_set_exchange(vglb_ctx *ctx, vglb_graph *g, int mode);
 
 #ifdef __cplusplus
 }

@@ -40,7 +40,10 @@ class GraphInfo(C.Structure):
     _fields_ = [("vertices", C.c_int32), ("edges", C.c_int64), ("has_incoming", C.c_int32), ("max_degree", C.c_int32),
                 ("tier_degree", C.c_int32 * NUM_TIERS), ("tier_border", C.c_int32 * NUM_TIERS),
                 ("d_out_ptr", C.c_void_p), ("d_out_adj", C.c_void_p), ("d_in_ptr", C.c_void_p), ("d_in_adj", C.c_void_p),
-                ("d_orig_to_sorted", C.c_void_p), ("d_sorted_to_orig", C.c_void_p), ("d_edge_order", C.c_void_p)]
+                ("d_orig_to_sorted", C.c_void_p), ("d_sorted_to_orig", C.c_void_p), ("d_edge_order", C.c_void_p),
+                ("part_rank", C.c_int32), ("part_world", C.c_int32), ("rows_per_rank", C.c_int32),
+                ("col_of_row0", C.c_int32), ("vertices_global", C.c_int32), ("reserved", C.c_int32),
+                ("columns", C.c_int64), ("edges_global", C.c_int64)]
 
 
 class Stats(C.Structure):
@@ -105,7 +108,21 @@ _SIGNATURES = {
     "vglb_reduce_sum_i32": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int64)]),
     "vglb_reduce_sum_f32": (C.c_int, [_P, _P, _P, C.POINTER(C.c_double)]),
     "vglb_reduce_max_i32": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int32)]),
+    "vglb_comm_unique_id": (C.c_int, [_P]),
+    "vglb_comm_init": (C.c_int, [_P, C.c_int, C.c_int, _P, C.POINTER(_P)]),
+    "vglb_comm_init_detached": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
+    "vglb_comm_destroy": (C.c_int, [_P]),
+    "vglb_comm_barrier": (C.c_int, [_P]),
+    "vglb_comm_allgather": (C.c_int, [_P, _P, C.c_size_t]),
+    "vglb_comm_allreduce_sum_i64": (C.c_int, [_P, _P, C.c_int]),
+    "vglb_comm_allreduce_max_f64": (C.c_int, [_P, C.POINTER(C.c_double)]),
+    "vglb_graph_from_edges_partitioned": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "vglb_graph_from_generator_partitioned": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "vglb_graph_set_exchange": (C.c_int, [_P, _P, C.c_int]),
+    "vglb_graph_from_csr_partitioned": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.POINTER(_P)]),
 }
+UNIQUE_ID_BYTES = 128
+EXCHANGE_NCCL, EXCHANGE_P2P = 0, 1
 
 
 def lib() -> C.CDLL:
@@ -197,6 +214,41 @@ class Context:
         return src, dst
 
 
+class Comm:
+    """NCCL communicator of this rank inside libvgl_b200 (vgl_mpi_init twin, library_data/init.hpp:5-38). The unique id
+    is created on rank 0 and handed to the other ranks by the caller (`exchange`: bytes on rank 0 -> bytes everywhere;
+    bench.py / the tests use a torch.distributed broadcast for that plumbing)."""
+
+    def __init__(self, ctx: Context, rank: int, world: int, exchange=None, detached: bool = False):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self.h = _P()
+        if detached:
+            _check(lib().vglb_comm_init_detached(ctx.h, rank, world, C.byref(self.h)))
+            return
+        uid = C.create_string_buffer(UNIQUE_ID_BYTES)
+        if rank == 0:
+            _check(lib().vglb_comm_unique_id(uid))
+        raw = bytes(uid.raw)
+        if world > 1:
+            if exchange is None:
+                raise VglbError("Comm: world > 1 needs an `exchange` callable to distribute the NCCL unique id")
+            raw = exchange(raw if rank == 0 else None)
+        _check(lib().vglb_comm_init(ctx.h, rank, world, raw, C.byref(self.h)))
+
+    def barrier(self):
+        _check(lib().vglb_comm_barrier(self.h))
+
+    def max_float(self, x: float) -> float:
+        v = C.c_double(x)
+        _check(lib().vglb_comm_allreduce_max_f64(self.h, C.byref(v)))
+        return v.value
+
+    def close(self):
+        if self.h:
+            lib().vglb_comm_destroy(self.h)
+            self.h = _P()
+
+
 class DeviceArray:
     """HBM-resident flat array (VerticesArray / EdgesArray storage; MemoryAPI::allocate_array, memory_API.hpp:3-15)."""
 
@@ -254,6 +306,49 @@ class Graph:
         self.info = GraphInfo()
         _check(lib().vglb_graph_get_info(self.h, C.byref(self.info)))
         self.V, self.E = self.info.vertices, self.info.edges
+        # partitioned graphs: V / E are this rank's rows / edges; vertex state is indexed by column id
+        self.V_global, self.E_global, self.cols = self.info.vertices_global, self.info.edges_global, self.info.columns
+        self.rank, self.world, self.vp, self.col0 = self.info.part_rank, self.info.part_world, self.info.rows_per_rank, self.info.col_of_row0
+
+    @classmethod
+    def from_edges_partitioned(cls, ctx: Context, comm: "Comm", V: int, src, dst, flags: int = 0, symmetrize: bool = False) -> "Graph":
+        """This rank's part of the 1D-partitioned graph; every rank passes the same edge list (collective-free build)."""
+        on_device = isinstance(src, DeviceArray)
+        E = src.n if on_device else int(src.shape[0])
+        if not on_device:
+            src = np.ascontiguousarray(src, np.int32)
+            dst = np.ascontiguousarray(dst, np.int32)
+        h = _P()
+        _check(lib().vglb_graph_from_edges_partitioned(ctx.h, comm.h, V, E, _ptr(src), _ptr(dst), int(on_device),
+                                                       int(symmetrize), flags, C.byref(h)))
+        g = cls(ctx, h)
+        g.comm = comm
+        return g
+
+    @classmethod
+    def from_csr_partitioned(cls, ctx: Context, comm: "Comm", V_global: int, out_ptr, out_adj, orig_to_col, in_ptr=None,
+                             in_adj=None) -> "Graph":
+        """VGL_Graph::move_to_device for this rank's part (host arrays -> HBM)."""
+        rows = int(out_ptr.shape[0]) - 1
+        keep = [np.ascontiguousarray(out_ptr, np.int64), np.ascontiguousarray(out_adj, np.int32),
+                np.ascontiguousarray(orig_to_col, np.int32)]
+        for a, t in ((in_ptr, np.int64), (in_adj, np.int32)):
+            keep.append(None if a is None else np.ascontiguousarray(a, t))
+        h = _P()
+        _check(lib().vglb_graph_from_csr_partitioned(ctx.h, comm.h, V_global, rows, *[_ptr(a) for a in keep], C.byref(h)))
+        g = cls(ctx, h)
+        g.comm = comm
+        return g
+
+    @classmethod
+    def from_generator_partitioned(cls, ctx: Context, comm: "Comm", kind: int, scale: int, edge_factor: int, flags: int = 0,
+                                   symmetrize: bool = False, seed: int = MASTER_SEED, abc=(57, 19, 19)) -> "Graph":
+        h = _P()
+        _check(lib().vglb_graph_from_generator_partitioned(ctx.h, comm.h, kind, scale, edge_factor << scale, seed, abc[0], abc[1],
+                                                           abc[2], int(symmetrize), flags, C.byref(h)))
+        g = cls(ctx, h)
+        g.comm = comm
+        return g
 
     @classmethod
     def from_edges(cls, ctx: Context, V: int, src, dst, flags: int = 0) -> "Graph":
@@ -298,14 +393,17 @@ class Graph:
     def layout(self, incoming: bool = False):
         i = self.info
         if incoming:
-            return self._d2h(i.d_in_ptr, self.V + 1, np.int64), self._d2h(i.d_in_adj, self.E, np.int32)
+            ptr = self._d2h(i.d_in_ptr, self.V + 1, np.int64)
+            return ptr, self._d2h(i.d_in_adj, int(ptr[-1]), np.int32)
         return self._d2h(i.d_out_ptr, self.V + 1, np.int64), self._d2h(i.d_out_adj, self.E, np.int32)
 
     def orig_to_sorted(self):
-        return self._d2h(self.info.d_orig_to_sorted, self.V, np.int32)
+        """ORIGINAL id -> SCATTER id (the column id on a partitioned graph)."""
+        return self._d2h(self.info.d_orig_to_sorted, self.V_global, np.int32)
 
     def sorted_to_orig(self):
-        return self._d2h(self.info.d_sorted_to_orig, self.V, np.int32)
+        """column id -> ORIGINAL id (-1 for the padding columns of a partitioned graph)."""
+        return self._d2h(self.info.d_sorted_to_orig, self.cols, np.int32)
 
     def tiers(self):
         return list(self.info.tier_degree), list(self.info.tier_border)
@@ -317,12 +415,16 @@ class Graph:
 
     def reorder(self, arr: DeviceArray, from_dir: int, to_dir: int) -> DeviceArray:
         assert arr.dtype.itemsize == 4
-        out = self.ctx.empty(arr.n, arr.dtype)
+        out = self.ctx.empty(self.V_global if to_dir == ORIGINAL else self.V, arr.dtype)
         _check(lib().vglb_varray_reorder_u32(self.ctx.h, self.h, arr.ptr, out.ptr, from_dir, to_dir))
         return out
 
+    def set_exchange(self, mode: int):
+        _check(lib().vglb_graph_set_exchange(self.ctx.h, self.h, mode))
+
     def to_original(self, arr: DeviceArray) -> np.ndarray:
-        """VerticesArray::reorder(ORIGINAL) + move_to_host."""
+        """VerticesArray::reorder(ORIGINAL) + move_to_host (a collective on a partitioned graph: every rank gets the
+        whole array)."""
         return self.reorder(arr, SCATTER, ORIGINAL).to_numpy()
 
     def synthetic_weights(self, seed: int) -> DeviceArray:

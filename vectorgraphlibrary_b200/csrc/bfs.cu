@@ -30,7 +30,9 @@
 
 // NT threads (a CTA, a warp or an 8-lane group) expand the out-row [s,e) of one frontier vertex.
 // Every thread of the warp must call this together (ballots inside); `e <= s` for idle groups.
-template <int NT>
+// PART = the graph is one rank's part: `visited` is the replicated bitmap (read only here) and discoveries are only
+// marked in the candidate bitmap `levels` points to (reinterpreted) — owners resolve them after the exchange.
+template <int NT, bool PART>
 __device__ __forceinline__ void td_expand(const int32_t *__restrict__ adj, int64_t s, int64_t e, int tid,
                                           uint32_t *__restrict__ visited, int32_t *__restrict__ levels, int32_t next_level,
                                           int32_t b0, int32_t b1, const TierQueues &nq, unsigned long long *counters)
@@ -45,17 +47,26 @@ __device__ __forceinline__ void td_expand(const int32_t *__restrict__ adj, int64
         {
             v = adj[p];
             const uint32_t bit = 1u << (v & 31);
-            if (!(visited[v >> 5] & bit))
+            if (PART)
             {
-                const uint32_t old = atomicOr(&visited[v >> 5], bit);
-                won = !(old & bit);
+                uint32_t *cand = reinterpret_cast<uint32_t *>(levels);
+                if (!(visited[v >> 5] & bit) && !(cand[v >> 5] & bit)) atomicOr(&cand[v >> 5], bit);
             }
-            if (won) levels[v] = next_level;
+            else
+            {
+                if (!(visited[v >> 5] & bit))
+                {
+                    const uint32_t old = atomicOr(&visited[v >> 5], bit);
+                    won = !(old & bit);
+                }
+                if (won) levels[v] = next_level;
+            }
         }
-        enqueue_binned(won, v, b0, b1, nq, counters);
+        if (!PART) enqueue_binned(won, v, b0, b1, nq, counters);
     }
 }
 
+template <bool PART>
 __global__ void __launch_bounds__(BFS_THREADS)
 bfs_td_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, TierQueues cq, int32_t n_big, int32_t n_mid,
               int32_t n_small, int32_t blocks_mid, int32_t blocks_small, uint32_t *__restrict__ visited,
@@ -70,7 +81,7 @@ bfs_td_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, 
         const int32_t u = cq.q[0][b];
         const int64_t s = ptr[u], e = ptr[u + 1];
         if (threadIdx.x == 0) edges = e - s;
-        td_expand<BFS_THREADS>(adj, s, e, threadIdx.x, visited, levels, next_level, b0, b1, nq, counters);
+        td_expand<BFS_THREADS, PART>(adj, s, e, threadIdx.x, visited, levels, next_level, b0, b1, nq, counters);
     }
     else if (b < n_big + blocks_mid)
     {
@@ -80,7 +91,7 @@ bfs_td_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, 
             const int32_t u = cq.q[1][i];
             const int64_t s = ptr[u], e = ptr[u + 1];
             if (lane == 0) edges += e - s;
-            td_expand<32>(adj, s, e, lane, visited, levels, next_level, b0, b1, nq, counters);
+            td_expand<32, PART>(adj, s, e, lane, visited, levels, next_level, b0, b1, nq, counters);
         }
     }
     else
@@ -102,7 +113,7 @@ bfs_td_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, 
                 e = ptr[u + 1];
                 if (gl == 0) edges += e - s;
             }
-            td_expand<G>(adj, s, e, gl, visited, levels, next_level, b0, b1, nq, counters);
+            td_expand<G, PART>(adj, s, e, gl, visited, levels, next_level, b0, b1, nq, counters);
         }
     }
     edges = warp_sum_i64(edges);
@@ -272,6 +283,255 @@ __global__ void bfs_init_kernel(int32_t *levels, uint32_t *visited, int32_t sour
     *queue_slot = source;
 }
 
+
+// ---- 1D-partitioned BFS (one rank's part; every rank runs the same host loop on the same allreduced counters) -------
+// Reference: the NEC backend replicates levels and MPI_Allreduce(MAX)es the whole int array after every advance
+// (vgl_compute_api/common/mpi_exchange.hpp:155-271). Here only bitmaps travel:
+//   top-down : each rank expands the frontier vertices it owns and marks every unvisited destination in a full-length
+//              candidate bitmap; an all-to-all hands slice q of every rank's candidates to rank q, which ORs them, masks
+//              its visited slice, writes the levels it owns and queues its new frontier vertices (bfs_combine_kernel);
+//   bottom-up: each rank scans the in-rows of the unvisited vertices it owns against the replicated frontier bitmap
+//              (same kernel as on one GPU, pointed at the owned slice);
+//   both     : the owned slices of the new frontier are allgathered (V/8 bytes in total) and ORed into the replicated
+//              visited bitmap; {found, m_f, edges, rows} are allreduced and drive termination and the alpha/beta switch.
+
+__global__ void bfs_part_init_kernel(uint32_t *visited, uint32_t *cur_bm, int32_t source_col, int32_t *levels_local,
+                                     int32_t local_row /* -1 unless owned */, int32_t *queue_slot)
+{
+    visited[source_col >> 5] = 1u << (source_col & 31);
+    cur_bm[source_col >> 5] = 1u << (source_col & 31);
+    if (local_row >= 0)
+    {
+        levels_local[local_row] = VGLB_FIRST_LEVEL_VERTEX;
+        *queue_slot = local_row;
+    }
+}
+
+// one thread per word of the owned slice: OR of the P received candidate slices, minus the visited ones
+__global__ void __launch_bounds__(256)
+bfs_combine_kernel(const uint32_t *__restrict__ stage, int32_t P, int32_t wslice, const uint32_t *__restrict__ visited_slice,
+                   uint32_t *__restrict__ next_slice, const int64_t *__restrict__ ptr, int32_t *__restrict__ levels_local,
+                   int32_t next_level, int32_t b0, int32_t b1, TierQueues nq, unsigned long long *counters)
+{
+    const int lane = threadIdx.x & 31;
+    const int32_t wpad = (wslice + 31) & ~31;
+    long long mf = 0;
+    int found = 0;
+    for (int32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < wpad; w += gridDim.x * blockDim.x)
+    {
+        uint32_t bits = 0;
+        if (w < wslice)
+        {
+            for (int p = 0; p < P; p++) bits |= stage[(int64_t)p * wslice + w];
+            bits &= ~visited_slice[w];
+            next_slice[w] = bits;
+            found += __popc(bits);
+        }
+        while (__any_sync(0xffffffffu, bits != 0))
+        {
+            const bool has = bits != 0;
+            int32_t row = 0;
+            if (has)
+            {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                row = (w << 5) + b;
+                levels_local[row] = next_level;
+                mf += ptr[row + 1] - ptr[row];
+            }
+            enqueue_binned(has, row, b0, b1, nq, counters);
+        }
+    }
+    mf = warp_sum_i64(mf);
+    found = (int)warp_sum_i64(found);
+    if (lane == 0)
+    {
+        if (mf) atomicAdd(&counters[C_MF], (unsigned long long)mf);
+        if (found) atomicAdd(&counters[C_FOUND], (unsigned long long)found);
+    }
+}
+
+__global__ void bfs_or_kernel(uint32_t *__restrict__ visited, const uint32_t *__restrict__ next_bm, int64_t words)
+{
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (int64_t)gridDim.x * blockDim.x)
+    {
+        const uint32_t n = next_bm[w];
+        if (n) visited[w] |= n;
+    }
+}
+
+__global__ void bfs_copy_counters_kernel(unsigned long long *c)
+{
+    if (threadIdx.x < C_COUNT) c[C_COUNT + threadIdx.x] = c[threadIdx.x];
+}
+
+static int bfs_partitioned(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t *d_levels, const vglb_bfs_opts *opts,
+                           vglb_stats *stats)
+{
+    VGLB_REQUIRE(source >= 0 && source < g->cols, "vglb_bfs: source column out of range");
+    const bool dopt = opts && opts->direction_optimising;
+    if (dopt && !g->d_in_ptr)
+    {
+        vglb_set_error("vglb_bfs: direction-optimising BFS needs a graph built with VGLB_GRAPH_WITH_INCOMING");
+        return VGLB_EINVAL;
+    }
+    const long long alpha = (opts && opts->alpha > 0) ? opts->alpha : 15;
+    const long long beta = (opts && opts->beta > 0) ? opts->beta : 18;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    vglb_comm *comm = g->comm;
+    const int32_t P = g->part_world, rank = g->part_rank, vp = g->vp, rows = g->V;
+    const int32_t wslice = vp / 32;
+    const int64_t words = g->cols / 32, my = (int64_t)rank * wslice;
+    for (int i = 0; i < 3; i++)
+        if (!g->d_part_bm[i]) CUDA_TRY(cudaMalloc(&g->d_part_bm[i], (size_t)(words + 32) * 4));
+    if (!g->d_part_stage) CUDA_TRY(cudaMalloc(&g->d_part_stage, (size_t)(words + 32) * 4));
+    if (!g->d_queue[0]) CUDA_TRY(cudaMalloc(&g->d_queue[0], ((size_t)vp + 3) * 4));
+    const int64_t launches0 = ctx->launches;
+    const int32_t b0 = g->tier_border[0], b1 = g->tier_border[1];
+    unsigned long long *d_cnt = (unsigned long long *)ctx->d_counters;
+    unsigned long long *h_cnt = (unsigned long long *)ctx->h_counters;
+    cudaStream_t st = ctx->stream;
+    TierQueues cq;
+    cq.q[0] = g->d_queue[0];
+    cq.q[1] = g->d_queue[0] + b0;
+    cq.q[2] = g->d_queue[0] + b1;
+    uint32_t *visited = g->d_part_bm[0], *cur_bm = g->d_part_bm[1], *next_bm = g->d_part_bm[2];
+
+    CUDA_TRY(cudaEventRecord(ctx->ev_start, st));
+    if (rows > 0) CUDA_TRY(cudaMemsetAsync(d_levels, 0xFF, (size_t)rows * 4, st));
+    CUDA_TRY(cudaMemsetAsync(visited, 0, (size_t)words * 4, st));
+    CUDA_TRY(cudaMemsetAsync(cur_bm, 0, (size_t)words * 4, st));
+    CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 2 * C_COUNT * 8, st));
+    const bool own_source = source / vp == rank;
+    const int32_t src_row = own_source ? source - rank * vp : -1;
+    VGLB_REQUIRE(!own_source || src_row < rows, "vglb_bfs: source is a padding column");
+    const int src_tier = src_row < 0 ? 0 : (src_row < b0 ? 0 : (src_row < b1 ? 1 : 2));
+    bfs_part_init_kernel<<<1, 1, 0, st>>>(visited, cur_bm, source, d_levels, src_row, cq.q[src_tier]);
+    KERNEL_TRY();
+    ctx->launches++;
+
+    int32_t n[3] = {0, 0, 0};
+    if (own_source) n[src_tier] = 1;
+    long long n_cur = 1, visited_total = 1;
+    bool bottom_up = false;
+    int32_t level = VGLB_FIRST_LEVEL_VERTEX;
+    int64_t tot_edges = 0, tot_rows = 0, tot_frontier_bytes = 0, levels_run = 0;
+    int32_t bu_levels = 0;
+    const long long Vg = g->V_orig;
+    const long long factor = (g->E_global / (Vg > 0 ? Vg : 1)) / 2 > 0 ? (g->E_global / Vg) / 2 : 1;
+    const int max_blocks = ctx->sm_count * 16;
+    int rc;
+
+    while (n_cur > 0)
+    {
+        if (!bottom_up)
+        {
+            CUDA_TRY(cudaMemsetAsync(next_bm, 0, (size_t)words * 4, st)); // candidates
+            const int blocks_mid = (int)min((int64_t)max_blocks, ceil_div64(n[1], BFS_THREADS / 32));
+            const int blocks_small = (int)min((int64_t)max_blocks, ceil_div64(n[2], BFS_THREADS / BFS_SMALL_LANES));
+            const int64_t grid = (int64_t)n[0] + blocks_mid + blocks_small;
+            if (grid > 0)
+            {
+                bfs_td_kernel<true><<<(unsigned)grid, BFS_THREADS, 0, st>>>(g->d_out_ptr, g->d_out_adj, cq, n[0], n[1], n[2], blocks_mid,
+                                                                          blocks_small, visited, (int32_t *)next_bm, level + 1, b0, b1,
+                                                                          cq, d_cnt);
+                KERNEL_TRY();
+                ctx->launches++;
+            }
+            rc = vglb_comm_alltoall_async(comm, next_bm, g->d_part_stage, (size_t)wslice * 4);
+            if (rc != VGLB_OK) return rc;
+            bfs_combine_kernel<<<(unsigned)min((int64_t)max_blocks, ceil_div64(wslice, 256)), 256, 0, st>>>(
+                g->d_part_stage, P, wslice, visited + my, next_bm + my, g->d_out_ptr, d_levels, level + 1, b0, b1, cq, d_cnt);
+            KERNEL_TRY();
+            ctx->launches++;
+            tot_frontier_bytes += (int64_t)wslice * 4 * (2 * P + 2);
+        }
+        else
+        {
+            CUDA_TRY(cudaMemsetAsync(next_bm + my, 0, (size_t)wslice * 4, st));
+            bfs_bu_kernel<<<ctx->sm_count * 8, BFS_THREADS, 0, st>>>(g->d_in_ptr, g->d_in_adj, rows, visited + my, cur_bm,
+                                                                    next_bm + my, d_levels, level + 1, d_cnt);
+            KERNEL_TRY();
+            ctx->launches++;
+            bu_levels++;
+            tot_frontier_bytes += (int64_t)wslice * 4 * 3;
+        }
+        rc = vglb_comm_allgather_async(comm, next_bm, (size_t)wslice * 4);
+        if (rc != VGLB_OK) return rc;
+        bfs_or_kernel<<<(unsigned)min((int64_t)max_blocks, ceil_div64(words, 256)), 256, 0, st>>>(visited, next_bm, words);
+        KERNEL_TRY();
+        bfs_copy_counters_kernel<<<1, 32, 0, st>>>(d_cnt);
+        KERNEL_TRY();
+        ctx->launches += 2;
+        rc = vglb_comm_allreduce_async(comm, d_cnt + C_COUNT, C_COUNT, VGLB_DT_I64, VGLB_OP_SUM);
+        if (rc != VGLB_OK) return rc;
+        CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, 2 * C_COUNT * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 2 * C_COUNT * 8, st));
+        levels_run++;
+        const unsigned long long *gl = h_cnt + C_COUNT; // global sums
+        const long long n_next = (long long)gl[C_FOUND];
+        tot_edges += (int64_t)h_cnt[C_EDGES];
+        tot_rows += bottom_up ? (int64_t)h_cnt[C_ROWS] : (int64_t)n[0] + n[1] + n[2];
+        tot_frontier_bytes += words * 4 * 3; // allgathered frontier written, ORed into visited
+        visited_total += n_next;
+        if (n_next == 0) break;
+
+        bool next_bu = bottom_up;
+        if (dopt)
+        {
+            const long long unvisited = Vg - visited_total;
+            if (!bottom_up && n_cur < n_next)
+            {
+                if ((long long)gl[C_MF] >= (unvisited * factor + Vg) / alpha) next_bu = true;
+            }
+            else if (bottom_up && n_cur >= n_next)
+            {
+                if (n_next < (unvisited * factor + Vg) / (factor * beta)) next_bu = false;
+            }
+        }
+        if (!next_bu)
+        {
+            if (!bottom_up)
+            {
+                n[0] = (int32_t)h_cnt[C_NEXT_BIG]; n[1] = (int32_t)h_cnt[C_NEXT_MID]; n[2] = (int32_t)h_cnt[C_NEXT_SMALL];
+            }
+            else
+            {
+                bfs_bitmap_to_queue_kernel<<<(unsigned)min((int64_t)max_blocks, ceil_div64(wslice, 256)), 256, 0, st>>>(
+                    next_bm + my, rows, b0, b1, cq, d_cnt);
+                KERNEL_TRY();
+                ctx->launches++;
+                CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, 3 * 8, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+                n[0] = (int32_t)h_cnt[0]; n[1] = (int32_t)h_cnt[1]; n[2] = (int32_t)h_cnt[2];
+                CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 2 * C_COUNT * 8, st));
+            }
+        }
+        uint32_t *t = cur_bm; cur_bm = next_bm; next_bm = t;
+        bottom_up = next_bu;
+        n_cur = n_next;
+        level++;
+    }
+    CUDA_TRY(cudaEventRecord(ctx->ev_stop, st));
+    CUDA_TRY(cudaEventSynchronize(ctx->ev_stop));
+    if (stats)
+    {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop));
+        memset(stats, 0, sizeof(*stats));
+        stats->seconds = ms * 1e-3;
+        stats->iterations = levels_run;
+        stats->edges_inspected = tot_edges;      // this rank's
+        stats->vertices_processed = tot_rows;
+        stats->frontier_bytes = tot_frontier_bytes;
+        stats->algorithmic_bytes = 8 * tot_edges + 12 * tot_rows + tot_frontier_bytes;
+        stats->kernel_launches = ctx->launches - launches0;
+        stats->bottom_up_levels = bu_levels;
+    }
+    return VGLB_OK;
+}
+
 static int bfs_prepare(vglb_ctx *ctx, vglb_graph *g)
 {
     if (g->bfs_ready) return VGLB_OK;
@@ -289,6 +549,7 @@ extern "C" int vglb_bfs(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t *d
                         vglb_stats *stats)
 {
     VGLB_REQUIRE(ctx != NULL && g != NULL && d_levels != NULL, "vglb_bfs: NULL argument");
+    if (g->comm) return bfs_partitioned(ctx, g, source, d_levels, opts, stats);
     VGLB_REQUIRE(source >= 0 && source < g->V, "vglb_bfs: source out of range");
     const bool dopt = opts && opts->direction_optimising;
     if (dopt && !g->d_in_ptr)
@@ -346,7 +607,7 @@ extern "C" int vglb_bfs(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t *d
             const int blocks_mid = (int)min((int64_t)max_blocks, ceil_div64(n[1], BFS_THREADS / 32));
             const int blocks_small = (int)min((int64_t)max_blocks, ceil_div64(n[2], BFS_THREADS / BFS_SMALL_LANES));
             const int64_t grid = (int64_t)n[0] + blocks_mid + blocks_small;
-            bfs_td_kernel<<<(unsigned)grid, BFS_THREADS, 0, st>>>(g->d_out_ptr, g->d_out_adj, cq, n[0], n[1], n[2], blocks_mid,
+            bfs_td_kernel<false><<<(unsigned)grid, BFS_THREADS, 0, st>>>(g->d_out_ptr, g->d_out_adj, cq, n[0], n[1], n[2], blocks_mid,
                                                                  blocks_small, g->d_visited, d_levels, level + 1, b0, b1, nq,
                                                                  d_cnt);
             KERNEL_TRY();

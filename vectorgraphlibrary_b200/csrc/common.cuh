@@ -80,11 +80,33 @@ struct vglb_graph
     int64_t *d_pr_ve_ptr;
     int32_t pr_ve_segments;
     int32_t col_of_row0;        // column id of local row 0 (0 unless the graph is one rank's part of a partitioned graph)
+    // 1D partition (partition.cu). On one GPU: cols = V_orig = vp = V, E_global = E, comm = NULL.
+    // On a partitioned graph V / E are this rank's rows / edges; vertex state is indexed by COLUMN id in [0, cols):
+    // column = owner * vp + local row; d_fwd maps ORIGINAL id -> column, d_bwd column -> ORIGINAL id (-1 = padding).
+    struct vglb_comm *comm;
+    int32_t part_rank, part_world;
+    int32_t vp;                 // rows per rank (slice stride, a multiple of 32)
+    int32_t V_orig;             // vertices of the whole graph
+    int64_t cols;               // part_world * vp
+    int64_t E_global;
+    // partitioned-algorithm scratch (owned by the graph)
+    uint32_t *d_part_bm[3];     // full-length bitmaps: visited, candidates / current frontier, next frontier
+    uint32_t *d_part_stage;     // part_world received bitmap slices
+    uint32_t *d_part_vec;       // full-length 4-byte vertex state (dist / labels)
+    uint32_t *d_part_prev;      // this rank's slice of the previous round's state
     // BFS / SSSP / CC scratch
     uint32_t *d_visited, *d_front_bm[2];
     int32_t *d_queue[2];
     int32_t *d_scratch_i32;
     int bfs_ready;
+};
+
+// NCCL communicator of one rank (partition.cu); the library dlopen()s libnccl.so.2 on first use
+struct vglb_comm
+{
+    void *nccl;        // ncclComm_t
+    int rank, world;
+    vglb_ctx *ctx;
 };
 
 struct vglb_frontier
@@ -111,6 +133,15 @@ constexpr int32_t vglb_tier_degree(int t)
 }
 
 int vglb_graph_compute_tiers(vglb_ctx *ctx, vglb_graph *g);
+void vglb_graph_set_unpartitioned(vglb_graph *g);
+void vglb_graph_free_fields(vglb_graph *g);
+
+// collectives on the context stream (partition.cu); asynchronous, every rank must make the same call
+enum { VGLB_DT_I32 = 0, VGLB_DT_U32 = 1, VGLB_DT_I64 = 2, VGLB_DT_F64 = 3 };
+enum { VGLB_OP_SUM = 0, VGLB_OP_MIN = 1, VGLB_OP_MAX = 2 };
+int vglb_comm_allgather_async(vglb_comm *comm, void *d_buf, size_t bytes_per_rank);
+int vglb_comm_allreduce_async(vglb_comm *comm, void *d_buf, size_t count, int dtype, int op);
+int vglb_comm_alltoall_async(vglb_comm *comm, const void *d_send, void *d_recv, size_t bytes_per_rank);
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

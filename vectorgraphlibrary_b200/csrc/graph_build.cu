@@ -136,6 +136,18 @@ __global__ void tier_border_kernel(const int64_t *__restrict__ ptr, int32_t V, i
 } // namespace
 
 
+void vglb_graph_set_unpartitioned(vglb_graph *g)
+{
+    g->comm = NULL;
+    g->part_rank = 0;
+    g->part_world = 1;
+    g->vp = g->V;
+    g->V_orig = g->V;
+    g->cols = g->V;
+    g->E_global = g->E;
+    g->col_of_row0 = 0;
+}
+
 static int bits_for(int32_t V)
 {
     int b = 1;
@@ -174,8 +186,10 @@ int vglb_graph_compute_tiers(vglb_ctx *ctx, vglb_graph *g)
     return VGLB_OK;
 }
 
-static void graph_free_fields(vglb_graph *g)
+void vglb_graph_free_fields(vglb_graph *g)
 {
+    cudaFree(g->d_part_bm[0]); cudaFree(g->d_part_bm[1]); cudaFree(g->d_part_bm[2]); cudaFree(g->d_part_stage);
+    cudaFree(g->d_part_vec); cudaFree(g->d_part_prev);
     cudaFree(g->d_out_ptr); cudaFree(g->d_out_adj); cudaFree(g->d_in_ptr); cudaFree(g->d_in_adj);
     cudaFree(g->d_fwd); cudaFree(g->d_bwd); cudaFree(g->d_edge_order);
     cudaFree(g->d_pr_inv); cudaFree(g->d_pr_contrib[0]); cudaFree(g->d_pr_contrib[1]); cudaFree(g->d_pr_dangling); cudaFree(g->d_pr_tasks); cudaFree(g->d_pr_piece_partial); cudaFree(g->d_pr_piece_count); cudaFree(g->d_pr_ve_adj); cudaFree(g->d_pr_ve_ptr);
@@ -188,7 +202,7 @@ extern "C" int vglb_graph_free(vglb_ctx *ctx, vglb_graph *g)
     VGLB_REQUIRE(ctx != NULL, "vglb_graph_free: ctx is NULL");
     if (!g) return VGLB_OK;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    graph_free_fields(g);
+    vglb_graph_free_fields(g);
     cudaGetLastError();
     free(g);
     return VGLB_OK;
@@ -291,7 +305,7 @@ extern "C" int vglb_graph_from_edges(vglb_ctx *ctx, int32_t V, int64_t E, const 
     auto cleanup = [&]() {
         cudaFree(d_src_own); cudaFree(d_dst_own); cudaFree(d_deg); cudaFree(dk0); cudaFree(dk1); cudaFree(dv0);
         cudaFree(dv1); cudaFree(d_deg_sorted); cudaFree(tmp); cudaFree(d_bad); cudaFree(d_row_of_pos);
-        graph_free_fields(g);
+        vglb_graph_free_fields(g);
         free(g);
     };
     const int32_t *d_src = src, *d_dst = dst;
@@ -385,6 +399,7 @@ extern "C" int vglb_graph_from_edges(vglb_ctx *ctx, int32_t V, int64_t E, const 
         BUILD_TRY(build_incoming(ctx, V, E, g->d_out_adj, d_row_of_pos, g->d_in_adj));
     }
     BUILD_TRY(vglb_graph_compute_tiers(ctx, g));
+    vglb_graph_set_unpartitioned(g);
     cudaFree(d_src_own); cudaFree(d_dst_own); cudaFree(d_deg); cudaFree(d_deg_sorted); cudaFree(d_bad);
     cudaFree(d_row_of_pos);
     *out_graph = g;
@@ -403,7 +418,7 @@ extern "C" int vglb_graph_from_csr(vglb_ctx *ctx, int32_t V, int64_t E, const in
     if (!g) return VGLB_ENOMEM;
     g->V = V;
     g->E = E;
-    auto cleanup = [&]() { graph_free_fields(g); free(g); };
+    auto cleanup = [&]() { vglb_graph_free_fields(g); free(g); };
     const size_t eb = (size_t)(E ? E : 1) * 4;
     BUILD_CUDA(cudaMalloc(&g->d_out_ptr, ((size_t)V + 2) * 8));
     BUILD_CUDA(cudaMalloc(&g->d_out_adj, eb + 16));
@@ -429,6 +444,7 @@ extern "C" int vglb_graph_from_csr(vglb_ctx *ctx, int32_t V, int64_t E, const in
     invert_perm_kernel<<<vgrid, 256, 0, ctx->stream>>>(g->d_fwd, g->d_bwd, V);
     BUILD_CUDA(cudaGetLastError());
     BUILD_TRY(vglb_graph_compute_tiers(ctx, g));
+    vglb_graph_set_unpartitioned(g);
     *out_graph = g;
     return VGLB_OK;
 }
@@ -453,6 +469,13 @@ extern "C" int vglb_graph_get_info(vglb_graph *g, vglb_graph_info *info)
     info->d_orig_to_sorted = g->d_fwd;
     info->d_sorted_to_orig = g->d_bwd;
     info->d_edge_order = g->d_edge_order;
+    info->part_rank = g->part_rank;
+    info->part_world = g->part_world;
+    info->rows_per_rank = g->vp;
+    info->col_of_row0 = g->col_of_row0;
+    info->vertices_global = g->V_orig;
+    info->columns = g->cols;
+    info->edges_global = g->E_global;
     return VGLB_OK;
 }
 
@@ -494,15 +517,43 @@ extern "C" int vglb_varray_reorder_u32(vglb_ctx *ctx, vglb_graph *g, const uint3
 {
     VGLB_REQUIRE(ctx != NULL && g != NULL && d_in != NULL && d_out != NULL, "vglb_varray_reorder_u32: NULL argument");
     VGLB_REQUIRE(d_in != (const uint32_t *)d_out, "vglb_varray_reorder_u32: reorder is out-of-place");
-    const int32_t *index = NULL;
-    if (from_dir == VGLB_SCATTER && to_dir == VGLB_ORIGINAL) index = g->d_fwd;       // out[orig] = in[fwd[orig]]
-    else if (from_dir == VGLB_ORIGINAL && to_dir == VGLB_SCATTER) index = g->d_bwd;  // out[sorted] = in[bwd[sorted]]
-    else
+    const bool to_orig = from_dir == VGLB_SCATTER && to_dir == VGLB_ORIGINAL;
+    const bool to_sorted = from_dir == VGLB_ORIGINAL && to_dir == VGLB_SCATTER;
+    if (!to_orig && !to_sorted)
     {
         vglb_set_error("vglb_varray_reorder_u32: only ORIGINAL <-> SCATTER is supported on the device layout "
                        "(the incoming CSR shares the SCATTER numbering)");
         return VGLB_EINVAL;
     }
+    if (g->comm)
+    {
+        // partitioned graph: SCATTER arrays hold this rank's rows, ORIGINAL arrays the whole graph (collective call)
+        if (to_sorted)
+        {
+            if (g->V > 0)
+            {
+                reorder_gather_kernel<<<(unsigned)ceil_div64(g->V, 256), 256, 0, ctx->stream>>>(d_in, d_out, g->d_bwd + g->col_of_row0, g->V);
+                KERNEL_TRY();
+            }
+            ctx->launches++;
+            return VGLB_OK;
+        }
+        uint32_t *full = NULL;
+        CUDA_TRY(cudaMalloc(&full, (size_t)g->cols * 4));
+        CUDA_TRY(cudaMemsetAsync(full + g->col_of_row0, 0, (size_t)g->vp * 4, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(full + g->col_of_row0, d_in, (size_t)g->V * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        int rc = vglb_comm_allgather_async(g->comm, full, (size_t)g->vp * 4);
+        if (rc == VGLB_OK)
+        {
+            reorder_gather_kernel<<<(unsigned)ceil_div64(g->V_orig, 256), 256, 0, ctx->stream>>>(full, d_out, g->d_fwd, g->V_orig);
+            if (cudaGetLastError() != cudaSuccess) rc = VGLB_ECUDA;
+        }
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(full);
+        ctx->launches++;
+        return rc;
+    }
+    const int32_t *index = to_orig ? g->d_fwd : g->d_bwd; // out[orig] = in[fwd[orig]] / out[sorted] = in[bwd[sorted]]
     reorder_gather_kernel<<<(unsigned)ceil_div64(g->V, 256), 256, 0, ctx->stream>>>(d_in, d_out, index, g->V);
     KERNEL_TRY();
     ctx->launches++;
@@ -512,7 +563,7 @@ extern "C" int vglb_varray_reorder_u32(vglb_ctx *ctx, vglb_graph *g, const uint3
 // ---- EdgesArray synthetic weights (EdgesArray::set_all_random twin, deterministic) ---------------------------------
 
 __global__ void fill_weights_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj,
-                                    const int32_t *__restrict__ bwd, int32_t V, uint64_t seed, float *__restrict__ w)
+                                    const int32_t *__restrict__ bwd, int32_t V, int32_t col0, uint64_t seed, float *__restrict__ w)
 {
     // warp per row, lanes stride the row
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -520,7 +571,7 @@ __global__ void fill_weights_kernel(const int64_t *__restrict__ ptr, const int32
     for (int64_t v = warp; v < V; v += nwarps)
     {
         const int64_t s = ptr[v], e = ptr[v + 1];
-        const int32_t ov = bwd[v];
+        const int32_t ov = bwd[col0 + v];
         for (int64_t p = s + lane_id(); p < e; p += 32) w[p] = vglb_edge_weight(ov, bwd[adj[p]], seed);
     }
 }
@@ -528,7 +579,7 @@ __global__ void fill_weights_kernel(const int64_t *__restrict__ ptr, const int32
 extern "C" int vglb_earray_fill_synthetic_weights(vglb_ctx *ctx, vglb_graph *g, uint64_t seed, float *d_weights)
 {
     VGLB_REQUIRE(ctx != NULL && g != NULL && d_weights != NULL, "vglb_earray_fill_synthetic_weights: NULL argument");
-    fill_weights_kernel<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(g->d_out_ptr, g->d_out_adj, g->d_bwd, g->V, seed, d_weights);
+    fill_weights_kernel<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(g->d_out_ptr, g->d_out_adj, g->d_bwd, g->V, g->col_of_row0, seed, d_weights);
     KERNEL_TRY();
     ctx->launches++;
     return VGLB_OK;
@@ -555,6 +606,7 @@ __global__ void indegree_noloops_kernel(const int64_t *__restrict__ ptr, const i
 extern "C" int vglb_graph_indegree_noloops(vglb_ctx *ctx, vglb_graph *g, int32_t *d_indeg)
 {
     VGLB_REQUIRE(ctx != NULL && g != NULL && d_indeg != NULL, "vglb_graph_indegree_noloops: NULL argument");
+    VGLB_REQUIRE(g->comm == NULL, "vglb_graph_indegree_noloops: not available on a partitioned graph (in-degrees are counted by the partitioned build)");
     CUDA_TRY(cudaMemsetAsync(d_indeg, 0, (size_t)g->V * 4, ctx->stream));
     indegree_noloops_kernel<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(g->d_out_ptr, g->d_out_adj, g->V, d_indeg);
     KERNEL_TRY();

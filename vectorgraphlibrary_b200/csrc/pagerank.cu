@@ -50,7 +50,9 @@
 
 __device__ __forceinline__ float pr_gather(const PrParams &P, const L2Pol &pol, int32_t v)
 {
-    if (v >= PR_COLD_ID) return ld_gather_cold_f32(P.contrib_in + v, pol.keep);
+    // hubs have the smallest local rows of every rank's slice: column = owner * vp + local row
+    const uint32_t local = P.vp_mask ? ((uint32_t)v & P.vp_mask) : (P.vp ? (uint32_t)v % P.vp : (uint32_t)v);
+    if (local >= P.cold_local) return ld_gather_cold_f32(P.contrib_in + v, pol.keep);
     return ld_gather_f32(P.contrib_in + v, pol.keep);
 }
 
@@ -329,6 +331,23 @@ __global__ void pr_inverse_degree_kernel(const int32_t *__restrict__ indeg, int3
     }
 }
 
+// in-degree without self loops by column id, counted over this rank's rows (summed over ranks by the caller)
+__global__ void pr_part_indegree_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, int32_t rows,
+                                        int32_t col0, int32_t *__restrict__ indeg)
+{
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < rows; r += nwarps)
+    {
+        const int64_t s = ptr[r], e = ptr[r + 1];
+        for (int64_t p = s + (threadIdx.x & 31); p < e; p += 32)
+        {
+            const int32_t d = adj[p];
+            if (d != col0 + (int32_t)r) atomicAdd(&indeg[d], 1);
+        }
+    }
+}
+
 // r0 = 1/V (pr.hpp:40-45): contrib0 = r0*inv, dangling[0] = sum over inv==0 of r0/V
 __global__ void pr_init_kernel(const float *__restrict__ inv, int32_t V, float r0, float v_as_float,
                                float *__restrict__ contrib, double *__restrict__ dangling0)
@@ -495,15 +514,41 @@ static int pr_build_tail_copy(vglb_ctx *ctx, vglb_graph *g)
 
 int vglb_pr_prepare(vglb_ctx *ctx, vglb_graph *g, int iters)
 {
-    if (!g->d_pr_inv)
+    if (!g->d_pr_contrib[0])
+    {
+        // the gathered vector is indexed by column id: the whole (replicated) vector on a partitioned graph
+        CUDA_TRY(cudaMalloc(&g->d_pr_contrib[0], (size_t)g->cols * 4));
+        CUDA_TRY(cudaMalloc(&g->d_pr_contrib[1], (size_t)g->cols * 4));
+        CUDA_TRY(cudaMemsetAsync(g->d_pr_contrib[0], 0, (size_t)g->cols * 4, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(g->d_pr_contrib[1], 0, (size_t)g->cols * 4, ctx->stream));
+    }
+    if (!g->d_pr_inv && g->comm) // part uploaded by vglb_graph_from_csr_partitioned: count columns locally, allreduce(sum)
+    {
+        int32_t *d_indeg = NULL;
+        CUDA_TRY(cudaMalloc(&d_indeg, (size_t)g->cols * 4));
+        CUDA_TRY(cudaMemsetAsync(d_indeg, 0, (size_t)g->cols * 4, ctx->stream));
+        pr_part_indegree_kernel<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(g->d_out_ptr, g->d_out_adj, g->V, g->col_of_row0, d_indeg);
+        KERNEL_TRY();
+        int rc = vglb_comm_allreduce_async(g->comm, d_indeg, (size_t)g->cols, VGLB_DT_I32, VGLB_OP_SUM);
+        if (rc != VGLB_OK) { cudaFree(d_indeg); return rc; }
+        CUDA_TRY(cudaMalloc(&g->d_pr_inv, (size_t)g->vp * 4));
+        CUDA_TRY(cudaMemsetAsync(g->d_pr_inv, 0, (size_t)g->vp * 4, ctx->stream));
+        if (g->V > 0)
+        {
+            pr_inverse_degree_kernel<<<(unsigned)ceil_div64(g->V, 256), 256, 0, ctx->stream>>>(d_indeg + g->col_of_row0, g->V, g->d_pr_inv);
+            KERNEL_TRY();
+        }
+        ctx->launches += 2;
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_indeg);
+    }
+    if (!g->d_pr_inv) // (the partitioned build fills it from its degree pass)
     {
         int32_t *d_indeg = NULL;
         CUDA_TRY(cudaMalloc(&d_indeg, (size_t)g->V * 4));
         int rc = vglb_graph_indegree_noloops(ctx, g, d_indeg);
         if (rc != VGLB_OK) { cudaFree(d_indeg); return rc; }
         CUDA_TRY(cudaMalloc(&g->d_pr_inv, (size_t)g->V * 4));
-        CUDA_TRY(cudaMalloc(&g->d_pr_contrib[0], (size_t)g->V * 4));
-        CUDA_TRY(cudaMalloc(&g->d_pr_contrib[1], (size_t)g->V * 4));
         pr_inverse_degree_kernel<<<(unsigned)ceil_div64(g->V, 256), 256, 0, ctx->stream>>>(d_indeg, g->V, g->d_pr_inv);
         KERNEL_TRY();
         ctx->launches++;
@@ -583,43 +628,72 @@ extern "C" int vglb_pagerank(vglb_ctx *ctx, vglb_graph *g, int iters, float damp
     int rc = vglb_pr_prepare(ctx, g, iters);
     if (rc != VGLB_OK) return rc;
 
+    // On a partitioned graph (g->comm): V = this rank's rows, the vector is indexed by column id, and after every sweep
+    // the owned slices are allgathered (exchange_vertices_array, mpi_exchange.hpp:155-271) and the dangling mass
+    // allreduced — both enqueued on the context stream, no host synchronisation inside the loop.
     const int32_t V = g->V;
+    vglb_comm *comm = g->comm;
+    const int32_t col0 = g->col_of_row0;
     PrParams P;
     memset(&P, 0, sizeof(P));
     const int64_t nblocks = vglb_pr_plan(g, V, &P);
     VGLB_REQUIRE(nblocks < 0x7fffffffLL, "vglb_pagerank: grid too large");
     P.inv = g->d_pr_inv;
-    P.col_of_row0 = 0;
+    P.col_of_row0 = col0;
     P.npeers = 0;
     P.d = damping;
-    P.k = (float)((1.0 - (double)damping) / (double)((float)V)); // pr.hpp:37-38
-    P.v_as_float = (float)V;
+    P.v_as_float = (float)g->V_orig;
+    P.k = (float)((1.0 - (double)damping) / (double)P.v_as_float); // pr.hpp:37-38
+    if (comm)
+    {
+        P.vp = (uint32_t)g->vp;
+        P.vp_mask = (g->vp & (g->vp - 1)) == 0 ? (uint32_t)g->vp - 1u : 0u;
+        P.cold_local = (uint32_t)(PR_COLD_ID / g->part_world);
+    }
+    else
+        P.cold_local = PR_COLD_ID;
+    auto exchange = [&](float *vec, double *dangling) -> int {
+        if (!comm) return VGLB_OK;
+        int rc = vglb_comm_allgather_async(comm, vec, (size_t)g->vp * 4);
+        if (rc != VGLB_OK) return rc;
+        return vglb_comm_allreduce_async(comm, dangling, 1, VGLB_DT_F64, VGLB_OP_SUM);
+    };
 
     CUDA_TRY(cudaEventRecord(ctx->ev_start, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(g->d_pr_dangling, 0, (size_t)(iters + 1) * sizeof(double), ctx->stream));
-    const float r0 = (float)(1.0 / (double)V); // pr.hpp:42
+    const float r0 = (float)(1.0 / (double)g->V_orig); // pr.hpp:42
     if (iters == 0)
     {
-        pr_fill_kernel<<<(unsigned)ceil_div64(V, 256), 256, 0, ctx->stream>>>(d_ranks, V, r0);
-        KERNEL_TRY();
+        if (V > 0)
+        {
+            pr_fill_kernel<<<(unsigned)ceil_div64(V, 256), 256, 0, ctx->stream>>>(d_ranks, V, r0);
+            KERNEL_TRY();
+        }
         ctx->launches++;
     }
     else
     {
         pr_init_kernel<<<ctx->sm_count * 4, PR_THREADS, 0, ctx->stream>>>(g->d_pr_inv, V, r0, P.v_as_float,
-                                                                        g->d_pr_contrib[0], g->d_pr_dangling);
+                                                                        g->d_pr_contrib[0] + col0, g->d_pr_dangling);
         KERNEL_TRY();
         ctx->launches++;
+        rc = exchange(g->d_pr_contrib[0], g->d_pr_dangling);
+        if (rc != VGLB_OK) return rc;
     }
     for (int it = 0; it < iters; it++)
     {
         P.contrib_in = g->d_pr_contrib[it & 1];
-        P.contrib_out = g->d_pr_contrib[(it + 1) & 1];
+        P.contrib_out = g->d_pr_contrib[(it + 1) & 1] + col0;
         P.rank_out = (it == iters - 1) ? d_ranks : NULL;
         P.dangling_in = g->d_pr_dangling + it;
         P.dangling_out = g->d_pr_dangling + it + 1;
         rc = vglb_pr_launch_sweep(ctx, P, nblocks);
         if (rc != VGLB_OK) return rc;
+        if (it < iters - 1)
+        {
+            rc = exchange(g->d_pr_contrib[(it + 1) & 1], g->d_pr_dangling + it + 1);
+            if (rc != VGLB_OK) return rc;
+        }
     }
     CUDA_TRY(cudaEventRecord(ctx->ev_stop, ctx->stream));
     CUDA_TRY(cudaEventSynchronize(ctx->ev_stop));
@@ -633,7 +707,20 @@ extern "C" int vglb_pagerank(vglb_ctx *ctx, vglb_graph *g, int iters, float damp
         stats->edges_inspected = (int64_t)iters * g->E;
         stats->vertices_processed = (int64_t)iters * V;
         stats->algorithmic_bytes = (int64_t)iters * (8 * g->E + 16 * (int64_t)V) + (iters > 0 ? 4 * (int64_t)V : 0);
+        if (comm) stats->frontier_bytes = (int64_t)iters * g->cols * 4; // bytes of the vector every rank receives + sends
         stats->kernel_launches = ctx->launches - launches0;
+    }
+    return VGLB_OK;
+}
+
+extern "C" int vglb_graph_set_exchange(vglb_ctx *ctx, vglb_graph *g, int mode)
+{
+    VGLB_REQUIRE(ctx != NULL && g != NULL, "vglb_graph_set_exchange: NULL argument");
+    VGLB_REQUIRE(mode == VGLB_EXCHANGE_NCCL || mode == VGLB_EXCHANGE_P2P, "vglb_graph_set_exchange: bad mode");
+    if (mode == VGLB_EXCHANGE_P2P)
+    {
+        vglb_set_error("vglb_graph_set_exchange: the peer-store exchange is not available in this build");
+        return VGLB_EINVAL;
     }
     return VGLB_OK;
 }

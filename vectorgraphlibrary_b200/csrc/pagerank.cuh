@@ -58,6 +58,8 @@ struct PrParams
     int32_t npeers;
     int32_t interleave;            // mix heavy and tail blocks in the grid
     float k, d, v_as_float;
+    uint32_t vp, vp_mask;          // partitioned graphs: rows per rank (slice stride) and vp - 1 when vp is a power of two
+    uint32_t cold_local;           // gathers of local rows at or above this bypass L1 (PR_COLD_ID / ranks)
     // tail: rows [tail_first, zero_first) have degree 1..31 and are read from the padded column-major copy
     const int32_t *ve_adj;         // segment s: ve_adj[ve_ptr[s] + j*32 + lane] = j-th neighbour of row tail_first + 32 s + lane
     const int64_t *ve_ptr;         // ve_segments + 1 offsets

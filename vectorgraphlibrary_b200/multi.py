@@ -1,0 +1,165 @@
+"""1D-partitioned drivers (one process per GPU) for bench.py and the multi-rank tests, plus the host-side mirror of
+the partition arithmetic of csrc/partition.cu.
+
+Partition (see include/vgl_b200.h, "multi-GPU"): the reference's degree-sorted ids s = 0..V-1 are dealt round-robin,
+owner(s) = s mod P, local row = s div P; replicated vertex arrays are indexed by column id
+column(s) = (s mod P) * vp + s div P with vp = rows per rank rounded up to a multiple of 32.
+Reference: per-rank vertex ranges of the MPI build, vect_csr/mpi_api.hpp:6-26, get_api.hpp:66-94.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from .dist import _stats, pick_sources
+
+
+def rows_per_rank(V: int, P: int) -> int:
+    """Slice stride vp: ceil(V / P) rounded up to whole 32-bit bitmap words."""
+    return ((-(-V // P) + 31) // 32) * 32
+
+
+def local_rows(V: int, P: int, rank: int) -> int:
+    """Number of sorted ids rank, rank + P, ... below V."""
+    return (V - rank + P - 1) // P if V > rank else 0
+
+
+def column_of_sorted(s, P: int, vp: int):
+    s = np.asarray(s)
+    return (s % P) * vp + s // P
+
+
+def sorted_of_column(c, P: int, vp: int):
+    c = np.asarray(c)
+    return (c % vp) * P + c // vp
+
+
+def owner_of_column(c, vp: int):
+    return np.asarray(c) // vp
+
+
+class PartitionedRunner:
+    """N > 1: rank r owns the rows {s : s mod N == r} of a graph N times the single-GPU workload (weak scaling: scale +
+    log2 N, same edge factor), built in place from the counter-based generator (no edge list ever leaves a GPU)."""
+
+    weak = True
+    ncu_traffic = None
+
+    def __init__(self, vgl, ctx, comm, workload, kind, scale, ef, pr_iters):
+        self.vgl, self.ctx, self.workload, self.pr_iters = vgl, ctx, workload, pr_iters
+        self.tcomm = comm  # torch.distributed plumbing (unique id exchange, host barriers)
+        world, rank = comm.world, comm.rank
+        extra = int(np.log2(world))
+        if (1 << extra) != world:
+            raise SystemExit("bench.py: --gpus must be a power of two")
+        self.scale = scale + extra
+        self.comm = vgl.Comm(ctx, rank, world, exchange=lambda b: comm.broadcast_bytes(b, vgl.UNIQUE_ID_BYTES, 0))
+        flags = vgl.GRAPH_WITH_INCOMING if workload == "bfs" else 0
+        self.g = vgl.Graph.from_generator_partitioned(ctx, self.comm, kind, self.scale, ef, flags, symmetrize=(workload == "cc"))
+        g = self.g
+        self.V_total, self.E_total = g.V_global, g.E_global
+        self.adj_bytes_per_gpu = 4 * g.E
+        self.partition = (f"1D vertex partition over {world} GPUs: sorted ids dealt round-robin (owner = id mod {world}), "
+                          f"weak scaling (scale {self.scale}), rank 0 holds {g.V} rows / {g.E} edges")
+        self.dtype = "f32" if workload in ("pr", "sssp") else "int32"
+        self.iters_per_step = pr_iters if workload == "pr" else 1
+        self.edges_per_step = g.E_global * self.iters_per_step
+        self.out = ctx.empty(max(1, g.V), np.float32 if self.dtype == "f32" else np.int32)
+        self.dominant_kernel = {"pr": "pr_sweep_kernel", "bfs": "bfs_td_kernel + bfs_bu_kernel (whole run)",
+                                "sssp": "sssp_relax_kernel (whole run)", "cc": "advance_all_active_kernel<CcHookPartOp> (whole run)"}[workload]
+        self.weights = g.synthetic_weights(vgl.MASTER_SEED ^ 0x5555) if workload == "sssp" else None
+        self.sources = None
+        if workload in ("bfs", "sssp"):
+            # ORIGINAL ids with out-degree > 0, identical on every rank: out-degree of a column from the allgathered
+            # row lengths (setup only)
+            ptr, _ = g.layout()
+            deg_local = ctx.empty(g.vp, np.int32)
+            full = ctx.empty(g.cols, np.int32)
+            d = np.zeros(g.vp, np.int32)
+            d[:g.V] = np.diff(ptr)
+            host_full = np.zeros(g.cols, np.int32)
+            host_full[g.col0:g.col0 + g.vp] = d
+            full.copy_from_host(host_full)
+            vgl._check(vgl.lib().vglb_comm_allgather(self.comm.h, full.ptr, g.vp * 4))
+            ctx.synchronize()
+            deg_by_col = full.to_numpy()
+            fwd = g.orig_to_sorted()
+            orig = pick_sources(g.V_global, deg_by_col[fwd], 16, vgl.MASTER_SEED)
+            self.sources = [int(fwd[s]) for s in orig]
+            deg_local.free(); full.free()
+        self._host = None
+
+    def step(self, i):
+        w = self.workload
+        if w == "pr":
+            _, st = self.g.pagerank(self.pr_iters, 0.85, self.out)
+            return _stats(st, self.pr_iters, st.algorithmic_bytes)
+        if w == "bfs":
+            _, st = self.g.bfs(self.sources[i % len(self.sources)], True, self.out)
+        elif w == "sssp":
+            _, st = self.g.sssp(self.weights, self.sources[i % len(self.sources)], self.out)
+        else:
+            _, st = self.g.cc(self.out)
+        return _stats(st, 1, st.algorithmic_bytes)
+
+    # ---- end to end through the C ABI with HOST buffers: every rank uploads its own part ----
+    def _host_arrays(self):
+        if self._host is None:
+            vgl, g = self.vgl, self.g
+            ptr, adj = g.layout()
+            H = {"ptr": vgl.pinned_array(g.V + 1, np.int64), "adj": vgl.pinned_array(g.E, np.int32),
+                 "fwd": vgl.pinned_array(g.V_global, np.int32), "in_ptr": None, "in_adj": None, "w": None,
+                 "out": vgl.pinned_array(max(1, g.V), np.float32 if self.dtype == "f32" else np.int32)}
+            H["ptr"][:], H["adj"][:], H["fwd"][:] = ptr, adj, g.orig_to_sorted()
+            del ptr, adj
+            if self.workload == "bfs":
+                iptr, iadj = g.layout(incoming=True)
+                H["in_ptr"], H["in_adj"] = vgl.pinned_array(g.V + 1, np.int64), vgl.pinned_array(len(iadj), np.int32)
+                H["in_ptr"][:], H["in_adj"][:] = iptr, iadj
+            if self.workload == "sssp":
+                H["w"] = vgl.pinned_array(g.E, np.float32)
+                H["w"][:] = self.weights.to_numpy()
+            self._host = H
+        return self._host
+
+    def e2e(self, steps):
+        vgl, ctx = self.vgl, self.ctx
+        H = self._host_arrays()
+        L = vgl.lib()
+        h2d = sum(H[k].nbytes for k in ("ptr", "adj", "fwd", "in_ptr", "in_adj", "w") if H[k] is not None)
+        d2h = H["out"].nbytes
+        times = []
+        for i in range(steps + 1):
+            self.comm.barrier()
+            t0 = time.perf_counter()
+            g = vgl.Graph.from_csr_partitioned(ctx, self.comm, self.g.V_global, H["ptr"], H["adj"], H["fwd"], H["in_ptr"], H["in_adj"])
+            out = ctx.empty(max(1, g.V), H["out"].dtype)
+            if self.workload == "pr":
+                g.pagerank(self.pr_iters, 0.85, out)
+            elif self.workload == "bfs":
+                g.bfs(self.sources[i % len(self.sources)], True, out)
+            elif self.workload == "sssp":
+                w = ctx.empty(g.E, np.float32)
+                vgl._check(L.vglb_memcpy_h2d(ctx.h, w.ptr, H["w"].ctypes.data, H["w"].nbytes))
+                g.sssp(w, self.sources[i % len(self.sources)], out)
+                w.free()
+            else:
+                g.cc(out)
+            vgl._check(L.vglb_memcpy_d2h(ctx.h, H["out"].ctypes.data, out.ptr, d2h))
+            ctx.synchronize()
+            self.comm.barrier()
+            dt = time.perf_counter() - t0
+            out.free()
+            g.free()
+            if i > 0:
+                times.append(dt)
+        # bytes of the whole job: every rank moves its own part
+        return {"seconds": float(np.mean(times)), "h2d": int(self.tcomm.sum_int(h2d)), "d2h": int(self.tcomm.sum_int(d2h))}
+
+    def extras(self):
+        return {"rows_rank0": self.g.V, "edges_rank0": self.g.E, "columns": self.g.cols}
+
+    def close(self):
+        self.g.free()
+        self.comm.close()
