@@ -94,6 +94,9 @@ struct vglb_graph
     uint32_t *d_part_stage;     // part_world received bitmap slices
     uint32_t *d_part_vec;       // full-length 4-byte vertex state (dist / labels)
     uint32_t *d_part_prev;      // this rank's slice of the previous round's state
+    // PageRank peer-store exchange: the peers' copies of the two contribution vectors (CUDA IPC mappings)
+    int pr_exchange;            // VGLB_EXCHANGE_NCCL | VGLB_EXCHANGE_P2P
+    float *d_pr_peer[2][8];     // [buffer][peer rank]; NULL for this rank
     // BFS / SSSP / CC scratch
     uint32_t *d_visited, *d_front_bm[2];
     int32_t *d_queue[2];

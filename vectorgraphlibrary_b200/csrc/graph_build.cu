@@ -190,6 +190,9 @@ void vglb_graph_free_fields(vglb_graph *g)
 {
     cudaFree(g->d_part_bm[0]); cudaFree(g->d_part_bm[1]); cudaFree(g->d_part_bm[2]); cudaFree(g->d_part_stage);
     cudaFree(g->d_part_vec); cudaFree(g->d_part_prev);
+    for (int b = 0; b < 2; b++)
+        for (int p = 0; p < 8; p++)
+            if (g->d_pr_peer[b][p]) cudaIpcCloseMemHandle(g->d_pr_peer[b][p]);
     cudaFree(g->d_out_ptr); cudaFree(g->d_out_adj); cudaFree(g->d_in_ptr); cudaFree(g->d_in_adj);
     cudaFree(g->d_fwd); cudaFree(g->d_bwd); cudaFree(g->d_edge_order);
     cudaFree(g->d_pr_inv); cudaFree(g->d_pr_contrib[0]); cudaFree(g->d_pr_contrib[1]); cudaFree(g->d_pr_dangling); cudaFree(g->d_pr_tasks); cudaFree(g->d_pr_piece_partial); cudaFree(g->d_pr_piece_count); cudaFree(g->d_pr_ve_adj); cudaFree(g->d_pr_ve_ptr);

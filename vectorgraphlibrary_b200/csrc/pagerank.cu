@@ -652,10 +652,17 @@ extern "C" int vglb_pagerank(vglb_ctx *ctx, vglb_graph *g, int iters, float damp
     }
     else
         P.cold_local = PR_COLD_ID;
-    auto exchange = [&](float *vec, double *dangling) -> int {
+    // exchange of the owned slices after a sweep: ncclAllGather, or nothing when the sweep's epilogue already stored
+    // them into the peers' vectors (then the dangling-mass allreduce is also the barrier between sweeps: a rank starts
+    // sweep i+1 only after every peer finished sweep i, i.e. finished both reading buffer i and writing buffer i+1)
+    const bool p2p = comm && g->pr_exchange == VGLB_EXCHANGE_P2P;
+    auto exchange = [&](float *vec, double *dangling, bool stored_by_peers) -> int {
         if (!comm) return VGLB_OK;
-        int rc = vglb_comm_allgather_async(comm, vec, (size_t)g->vp * 4);
-        if (rc != VGLB_OK) return rc;
+        if (!stored_by_peers)
+        {
+            int rc = vglb_comm_allgather_async(comm, vec, (size_t)g->vp * 4);
+            if (rc != VGLB_OK) return rc;
+        }
         return vglb_comm_allreduce_async(comm, dangling, 1, VGLB_DT_F64, VGLB_OP_SUM);
     };
 
@@ -677,7 +684,7 @@ extern "C" int vglb_pagerank(vglb_ctx *ctx, vglb_graph *g, int iters, float damp
                                                                         g->d_pr_contrib[0] + col0, g->d_pr_dangling);
         KERNEL_TRY();
         ctx->launches++;
-        rc = exchange(g->d_pr_contrib[0], g->d_pr_dangling);
+        rc = exchange(g->d_pr_contrib[0], g->d_pr_dangling, false);
         if (rc != VGLB_OK) return rc;
     }
     for (int it = 0; it < iters; it++)
@@ -687,11 +694,17 @@ extern "C" int vglb_pagerank(vglb_ctx *ctx, vglb_graph *g, int iters, float damp
         P.rank_out = (it == iters - 1) ? d_ranks : NULL;
         P.dangling_in = g->d_pr_dangling + it;
         P.dangling_out = g->d_pr_dangling + it + 1;
+        P.npeers = 0;
+        if (p2p && it < iters - 1)
+            for (int p = 0; p < g->part_world; p++)
+                if (p != g->part_rank) P.peer_out[P.npeers++] = g->d_pr_peer[(it + 1) & 1][p] + col0;
         rc = vglb_pr_launch_sweep(ctx, P, nblocks);
         if (rc != VGLB_OK) return rc;
-        if (it < iters - 1)
+        if (it < iters - 1 || p2p)
         {
-            rc = exchange(g->d_pr_contrib[(it + 1) & 1], g->d_pr_dangling + it + 1);
+            // (with peer stores the last sweep still ends in the allreduce: no rank may start its NEXT run — which
+            // rewrites buffer 0 everywhere — before every peer has finished reading)
+            rc = exchange(g->d_pr_contrib[(it + 1) & 1], g->d_pr_dangling + it + 1, p2p);
             if (rc != VGLB_OK) return rc;
         }
     }
@@ -713,14 +726,54 @@ extern "C" int vglb_pagerank(vglb_ctx *ctx, vglb_graph *g, int iters, float damp
     return VGLB_OK;
 }
 
+// Peer-store exchange: map every peer's two contribution vectors into this process (CUDA IPC over NVLink peer access).
+// The handles travel through the communicator itself (an allgather of 2 x 64 bytes per rank).
 extern "C" int vglb_graph_set_exchange(vglb_ctx *ctx, vglb_graph *g, int mode)
 {
     VGLB_REQUIRE(ctx != NULL && g != NULL, "vglb_graph_set_exchange: NULL argument");
     VGLB_REQUIRE(mode == VGLB_EXCHANGE_NCCL || mode == VGLB_EXCHANGE_P2P, "vglb_graph_set_exchange: bad mode");
-    if (mode == VGLB_EXCHANGE_P2P)
+    if (mode == VGLB_EXCHANGE_NCCL || !g->comm || g->part_world == 1)
     {
-        vglb_set_error("vglb_graph_set_exchange: the peer-store exchange is not available in this build");
-        return VGLB_EINVAL;
+        g->pr_exchange = VGLB_EXCHANGE_NCCL;
+        return VGLB_OK;
     }
+    VGLB_REQUIRE(g->part_world <= PR_MAX_PEERS, "vglb_graph_set_exchange: at most 8 ranks for the peer-store exchange");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (!g->d_pr_peer[0][(g->part_rank + 1) % g->part_world])
+    {
+        int rc = vglb_pr_prepare(ctx, g, 1);
+        if (rc != VGLB_OK) return rc;
+        const int P = g->part_world, rank = g->part_rank;
+        const size_t hb = sizeof(cudaIpcMemHandle_t);
+        cudaIpcMemHandle_t mine[2];
+        CUDA_TRY(cudaIpcGetMemHandle(&mine[0], g->d_pr_contrib[0]));
+        CUDA_TRY(cudaIpcGetMemHandle(&mine[1], g->d_pr_contrib[1]));
+        char *d_all = NULL;
+        CUDA_TRY(cudaMalloc(&d_all, (size_t)P * 2 * hb));
+        CUDA_TRY(cudaMemcpyAsync(d_all + (size_t)rank * 2 * hb, mine, 2 * hb, cudaMemcpyHostToDevice, ctx->stream));
+        rc = vglb_comm_allgather_async(g->comm, d_all, 2 * hb);
+        if (rc != VGLB_OK) { cudaFree(d_all); return rc; }
+        cudaIpcMemHandle_t all[2 * PR_MAX_PEERS];
+        CUDA_TRY(cudaMemcpyAsync(all, d_all, (size_t)P * 2 * hb, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_all);
+        for (int p = 0; p < P; p++)
+        {
+            if (p == rank) continue;
+            for (int b = 0; b < 2; b++)
+            {
+                void *ptr = NULL;
+                cudaError_t e = cudaIpcOpenMemHandle(&ptr, all[2 * p + b], cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess)
+                {
+                    cudaGetLastError();
+                    vglb_set_error("vglb_graph_set_exchange: cudaIpcOpenMemHandle of rank %d failed: %s", p, cudaGetErrorString(e));
+                    return VGLB_ECUDA;
+                }
+                g->d_pr_peer[b][p] = (float *)ptr;
+            }
+        }
+    }
+    g->pr_exchange = VGLB_EXCHANGE_P2P;
     return VGLB_OK;
 }

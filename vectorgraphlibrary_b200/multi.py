@@ -58,10 +58,14 @@ class PartitionedRunner:
         flags = vgl.GRAPH_WITH_INCOMING if workload == "bfs" else 0
         self.g = vgl.Graph.from_generator_partitioned(ctx, self.comm, kind, self.scale, ef, flags, symmetrize=(workload == "cc"))
         g = self.g
+        self.exchange = "n/a"
+        if workload == "pr":
+            self.exchange = self._choose_exchange(g)
         self.V_total, self.E_total = g.V_global, g.E_global
         self.adj_bytes_per_gpu = 4 * g.E
         self.partition = (f"1D vertex partition over {world} GPUs: sorted ids dealt round-robin (owner = id mod {world}), "
-                          f"weak scaling (scale {self.scale}), rank 0 holds {g.V} rows / {g.E} edges")
+                          f"weak scaling (scale {self.scale}), rank 0 holds {g.V} rows / {g.E} edges"
+                          + (f"; PageRank exchange: {self.exchange}" if workload == "pr" else ""))
         self.dtype = "f32" if workload in ("pr", "sssp") else "int32"
         self.iters_per_step = pr_iters if workload == "pr" else 1
         self.edges_per_step = g.E_global * self.iters_per_step
@@ -71,24 +75,52 @@ class PartitionedRunner:
         self.weights = g.synthetic_weights(vgl.MASTER_SEED ^ 0x5555) if workload == "sssp" else None
         self.sources = None
         if workload in ("bfs", "sssp"):
-            # ORIGINAL ids with out-degree > 0, identical on every rank: out-degree of a column from the allgathered
-            # row lengths (setup only)
-            ptr, _ = g.layout()
-            deg_local = ctx.empty(g.vp, np.int32)
-            full = ctx.empty(g.cols, np.int32)
-            d = np.zeros(g.vp, np.int32)
-            d[:g.V] = np.diff(ptr)
-            host_full = np.zeros(g.cols, np.int32)
-            host_full[g.col0:g.col0 + g.vp] = d
-            full.copy_from_host(host_full)
-            vgl._check(vgl.lib().vglb_comm_allgather(self.comm.h, full.ptr, g.vp * 4))
-            ctx.synchronize()
-            deg_by_col = full.to_numpy()
-            fwd = g.orig_to_sorted()
-            orig = pick_sources(g.V_global, deg_by_col[fwd], 16, vgl.MASTER_SEED)
-            self.sources = [int(fwd[s]) for s in orig]
-            deg_local.free(); full.free()
+            self.sources = self._pick_sources(16)
         self._host = None
+
+    def _pick_sources(self, count):
+        """`count` seeded ORIGINAL ids with out-degree > 0, as column ids; identical on every rank (vglb_source_candidate,
+        include/vglb_synth.h). The out-degree of a candidate is looked up in the allgathered row lengths on the device —
+        a few 4-byte reads instead of a V-sized host array."""
+        from .dist import mix64, _M64
+        vgl, g, ctx = self.vgl, self.g, self.ctx
+        ptr, _unused = g._d2h(g.info.d_out_ptr, g.V + 1, np.int64), None
+        host = np.zeros(g.cols, np.int32)
+        host[g.col0:g.col0 + g.V] = np.diff(ptr)
+        full = ctx.from_numpy(host)
+        del host, ptr
+        vgl._check(vgl.lib().vglb_comm_allgather(self.comm.h, full.ptr, g.vp * 4))
+        ctx.synchronize()
+        out, k, seed = [], 0, vgl.MASTER_SEED
+        while len(out) < count:
+            v = mix64(seed ^ ((0xA5A5A5A5 + k * 0x9E3779B97F4A7C15) & _M64)) % g.V_global
+            k += 1
+            col = int(g._d2h(g.info.d_orig_to_sorted + 4 * v, 1, np.int32)[0])
+            if int(g._d2h(full.ptr + 4 * col, 1, np.int32)[0]) > 0:
+                out.append(col)
+            if k > 64 * count + 1024:
+                raise RuntimeError("no vertex with out-degree > 0")
+        full.free()
+        return out
+
+    def _choose_exchange(self, g):
+        """Peer stores fused into the sweep (CUDA IPC over NVLink) unless VGLB_PR_EXCHANGE=nccl; every rank must end up
+        in the same mode, so a rank whose IPC mapping fails takes everybody back to ncclAllGather (and says so)."""
+        import os
+        import sys
+        vgl = self.vgl
+        if os.environ.get("VGLB_PR_EXCHANGE", "p2p") == "nccl":
+            return "ncclAllGather per sweep"
+        ok = 1
+        try:
+            g.set_exchange(vgl.EXCHANGE_P2P)
+        except vgl.VglbError as ex:
+            ok = 0
+            sys.stderr.write(f"[rank {self.tcomm.rank}] peer-store exchange unavailable: {ex}\n")
+        if self.tcomm.sum_int(ok) == self.tcomm.world:
+            return "peer stores from the sweep epilogue (CUDA IPC over NVLink) + allreduce of the dangling mass"
+        g.set_exchange(vgl.EXCHANGE_NCCL)
+        return "ncclAllGather per sweep (peer-store mapping failed)"
 
     def step(self, i):
         w = self.workload
