@@ -201,6 +201,8 @@ int vglb_frontier_get_info(vglb_ctx *ctx, vglb_frontier *f, vglb_frontier_info *
 /* generate_new_frontier (common/generate_new_frontier.hpp:4-43) with the predicates the four algorithms use:
  * flags given explicitly, `values[v] == key` (BFS on_next_level), `a[v] != b[v]` (SSSP changes_occurred). */
 int vglb_gnf_from_flags(vglb_ctx *ctx, vglb_frontier *f, const int32_t *d_flags);
+/* flags as a bitmap (bit v of word v/32): what the lambda shim's filter kernel produces (gnf_bitmap_kernel) */
+int vglb_gnf_from_bitmap(vglb_ctx *ctx, vglb_frontier *f, const uint32_t *d_bits);
 int vglb_gnf_eq_i32(vglb_ctx *ctx, vglb_frontier *f, const int32_t *d_values, int32_t key);
 int vglb_gnf_ne_u32(vglb_ctx *ctx, vglb_frontier *f, const uint32_t *d_a, const uint32_t *d_b);
 /* reduce (common/reduce.hpp:4-67): sum / max of a vertex array over the frontier */

@@ -94,9 +94,12 @@ __device__ __forceinline__ void advance_group_rows(const CsrView &g, int32_t row
 }
 
 // ALL_ACTIVE advance over every vertex (advance_worker ALL_ACTIVE branch, multicore/advance_worker.hpp:204-319)
-template <class EdgeOp, class PreOp, class PostOp>
+// The reference passes a second functor triple for the low-degree ("collective") region
+// (graph_abstractions.h:96-118, multicore/advance_all_active.hpp:150-229); here it serves the rows with < 32 edges.
+template <class EdgeOp, class PreOp, class PostOp, class CEdgeOp, class CPreOp, class CPostOp>
 __global__ void __launch_bounds__(kAdvThreads)
-advance_all_active_kernel(const CsrView g, const AllActivePlan P, long long edge_shift, EdgeOp edge_op, PreOp pre, PostOp post)
+advance_all_active_kernel(const CsrView g, const AllActivePlan P, long long edge_shift, EdgeOp edge_op, PreOp pre, PostOp post,
+                          CEdgeOp c_edge_op, CPreOp c_pre, CPostOp c_post)
 {
     const int b = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -126,11 +129,11 @@ advance_all_active_kernel(const CsrView g, const AllActivePlan P, long long edge
         const int32_t row1 = min(row0 + per, last);
         switch (t)
         {
-        case 2: advance_group_rows<16>(g, row0, row1, edge_shift, edge_op, pre, post); break;
-        case 3: advance_group_rows<8>(g, row0, row1, edge_shift, edge_op, pre, post); break;
-        case 4: advance_group_rows<4>(g, row0, row1, edge_shift, edge_op, pre, post); break;
-        case 5: advance_group_rows<2>(g, row0, row1, edge_shift, edge_op, pre, post); break;
-        default: advance_group_rows<1>(g, row0, row1, edge_shift, edge_op, pre, post); break;
+        case 2: advance_group_rows<16>(g, row0, row1, edge_shift, c_edge_op, c_pre, c_post); break;
+        case 3: advance_group_rows<8>(g, row0, row1, edge_shift, c_edge_op, c_pre, c_post); break;
+        case 4: advance_group_rows<4>(g, row0, row1, edge_shift, c_edge_op, c_pre, c_post); break;
+        case 5: advance_group_rows<2>(g, row0, row1, edge_shift, c_edge_op, c_pre, c_post); break;
+        default: advance_group_rows<1>(g, row0, row1, edge_shift, c_edge_op, c_pre, c_post); break;
         }
     }
 }
@@ -143,9 +146,10 @@ struct SparseFrontierView
     int32_t blocks_mid, blocks_small;
 };
 
-template <class EdgeOp, class PreOp, class PostOp>
+template <class EdgeOp, class PreOp, class PostOp, class CEdgeOp, class CPreOp, class CPostOp>
 __global__ void __launch_bounds__(kAdvThreads)
-advance_sparse_kernel(const CsrView g, const SparseFrontierView F, long long edge_shift, EdgeOp edge_op, PreOp pre, PostOp post)
+advance_sparse_kernel(const CsrView g, const SparseFrontierView F, long long edge_shift, EdgeOp edge_op, PreOp pre, PostOp post,
+                      CEdgeOp c_edge_op, CPreOp c_pre, CPostOp c_post)
 {
     const int b = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -166,8 +170,22 @@ advance_sparse_kernel(const CsrView g, const SparseFrontierView F, long long edg
         const int ngroups = F.blocks_small * GROUPS;
         const int gid = threadIdx.x / G, gl = threadIdx.x % G;
         for (int i = (b - F.n[0] - F.blocks_mid) * GROUPS + gid; i < F.n[2]; i += ngroups)
-            advance_row<G>(g, F.q[2][i], gl, edge_shift, edge_op, pre, post, [] { __syncwarp(__activemask()); });
+            advance_row<G>(g, F.q[2][i], gl, edge_shift, c_edge_op, c_pre, c_post, [] { __syncwarp(__activemask()); });
     }
+}
+
+// advance over a CSR whose rows are not degree-sorted (the incoming direction shares the outgoing numbering, so ids say
+// nothing about in-degrees): warp per row, optionally restricted to an id list.
+template <class EdgeOp, class PreOp, class PostOp>
+__global__ void __launch_bounds__(kAdvThreads)
+advance_unsorted_kernel(const CsrView g, const int32_t *__restrict__ ids, int32_t n, long long edge_shift, EdgeOp edge_op,
+                        PreOp pre, PostOp post)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < n; i += nwarps)
+        advance_row<32>(g, ids ? ids[i] : (int32_t)i, lane, edge_shift, edge_op, pre, post, [] { __syncwarp(); });
 }
 
 // compute (common/compute.hpp:62-85): map over all vertices / over a sparse id list

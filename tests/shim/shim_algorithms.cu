@@ -1,0 +1,246 @@
+// shim_algorithms.cu — BFS, SSSP, CC and PageRank written against the user-lambda operator API of
+// include/vgl_b200/graph_abstractions_b200.cuh, the way the reference's algorithms/* are written against
+// VGL_GRAPH_ABSTRACTIONS (operator sequences follow algorithms/bfs/bfs.hpp:5-51, sssp/shortest_paths.hpp:7-78,
+// cc/shiloach_vishkin.hpp:7-88, pr/pr.hpp:7-148). Test driver: builds a seeded synthetic graph, runs the four
+// algorithms through the generic (lambda) path and dumps the results in ORIGINAL numbering; tests/test_gpu_shim.py
+// compares them with the oracle. Also exercises the misuse errors (throw const char*).
+//
+//   shim_algorithms <kind> <scale> <edge_factor> <seed> <source_original_id> <weight_seed> <pr_iters> <out_dir>
+#include <cfloat>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "vgl_b200/graph_abstractions_b200.cuh"
+
+using namespace vglb;
+
+#define UNVISITED_VERTEX (-1)
+#define FIRST_LEVEL_VERTEX 1
+
+// ---- BFS, top-down: per level one scatter + one generate_new_frontier ------------------------------------------------
+static int bfs_top_down(GraphB200 &graph, GraphAbstractionsB200 &graph_API, FrontierB200 &frontier, VerticesArrayB200<int> &levels,
+                        int source_vertex)
+{
+    auto init_levels = [levels, source_vertex] __VGLB_COMPUTE_ARGS__ {
+        levels[src_id] = (src_id == source_vertex) ? FIRST_LEVEL_VERTEX : UNVISITED_VERTEX;
+    };
+    frontier.set_all_active();
+    graph_API.compute(graph, frontier, init_levels);
+    frontier.clear();
+    frontier.add_vertex(source_vertex);
+    int current_level = FIRST_LEVEL_VERTEX;
+    while (frontier.size() > 0)
+    {
+        auto edge_op = [levels, current_level] __VGLB_SCATTER_ARGS__ {
+            if (levels[src_id] == current_level && levels[dst_id] == UNVISITED_VERTEX) levels[dst_id] = current_level + 1;
+        };
+        graph_API.scatter(graph, frontier, edge_op);
+        auto on_next_level = [levels, current_level] __VGLB_GNF_ARGS__ {
+            return levels[src_id] == current_level + 1 ? IN_FRONTIER_FLAG : NOT_IN_FRONTIER_FLAG;
+        };
+        graph_API.generate_new_frontier(graph, frontier, on_next_level);
+        current_level++;
+    }
+    return current_level;
+}
+
+// ---- SSSP, frontier Bellman-Ford (partial-active push) ----------------------------------------------------------------
+static int sssp_partial_active(GraphB200 &graph, GraphAbstractionsB200 &graph_API, FrontierB200 &work_frontier, FrontierB200 &all_active,
+                               EdgesArrayB200<float> &weights, VerticesArrayB200<float> &distances, int source_vertex)
+{
+    VerticesArrayB200<float> prev_distances(graph);
+    const float inf_val = FLT_MAX - 100.0f; // shortest_paths.hpp:22
+    auto init_distances = [distances, source_vertex, inf_val] __VGLB_COMPUTE_ARGS__ {
+        distances[src_id] = (src_id == source_vertex) ? 0.0f : inf_val;
+    };
+    all_active.set_all_active();
+    graph_API.compute(graph, all_active, init_distances);
+    work_frontier.clear();
+    work_frontier.add_vertex(source_vertex);
+    int iterations = 0;
+    while (work_frontier.size() > 0)
+    {
+        auto save_old_distances = [distances, prev_distances] __VGLB_COMPUTE_ARGS__ { prev_distances[src_id] = distances[src_id]; };
+        graph_API.compute(graph, all_active, save_old_distances);
+        auto edge_op_push = [distances, weights] __VGLB_SCATTER_ARGS__ {
+            const float cand = distances[src_id] + weights[global_edge_pos];
+            // non-negative floats order like their bit patterns: the reference's racy "if (d[dst] > cand) d[dst] = cand"
+            // (shortest_paths.hpp:46-54) made atomic
+            if (cand < distances[dst_id]) atomicMin((unsigned int *)&distances[dst_id], __float_as_uint(cand));
+        };
+        graph_API.scatter(graph, work_frontier, edge_op_push);
+        auto changes_occurred = [distances, prev_distances] __VGLB_GNF_ARGS__ {
+            return distances[src_id] != prev_distances[src_id] ? IN_FRONTIER_FLAG : NOT_IN_FRONTIER_FLAG;
+        };
+        graph_API.generate_new_frontier(graph, work_frontier, changes_occurred);
+        iterations++;
+    }
+    return iterations;
+}
+
+// ---- CC, min-label hooking + pointer jumping ---------------------------------------------------------------------------
+static int cc_shiloach_vishkin(GraphB200 &graph, GraphAbstractionsB200 &graph_API, FrontierB200 &frontier, VerticesArrayB200<int> &components)
+{
+    VerticesArrayB200<int> before(graph);
+    frontier.set_all_active();
+    auto init_components = [components] __VGLB_COMPUTE_ARGS__ { components[src_id] = src_id; };
+    graph_API.compute(graph, frontier, init_components);
+    int rounds = 0;
+    for (;;)
+    {
+        auto remember = [components, before] __VGLB_COMPUTE_ARGS__ { before[src_id] = components[src_id]; };
+        graph_API.compute(graph, frontier, remember);
+        auto hook = [components] __VGLB_SCATTER_ARGS__ {
+            const int src_val = components[src_id];
+            if (src_val < components[dst_id]) atomicMin(&components[dst_id], src_val);
+        };
+        graph_API.scatter(graph, frontier, hook);
+        rounds++;
+        auto hook_changes = [components, before] __VGLB_REDUCE_INT_ARGS__ { return components[src_id] != before[src_id] ? 1 : 0; };
+        if (graph_API.reduce<int>(graph, frontier, hook_changes, REDUCE_SUM) == 0) break;
+        for (;;)
+        {
+            graph_API.compute(graph, frontier, remember);
+            auto jump = [components] __VGLB_COMPUTE_ARGS__ {
+                const int c = components[src_id];
+                const int cc = components[c];
+                if (cc != c) components[src_id] = cc;
+            };
+            graph_API.compute(graph, frontier, jump);
+            if (graph_API.reduce<int>(graph, frontier, hook_changes, REDUCE_SUM) == 0) break;
+        }
+    }
+    return rounds;
+}
+
+// ---- PageRank, multicore semantics: r'[u] = k + d * (sum_{u->v, v != u} r[v] / indeg_noloops(v) + dangling) ------------
+static void page_rank(GraphB200 &graph, GraphAbstractionsB200 &graph_API, FrontierB200 &frontier, VerticesArrayB200<float> &page_ranks,
+                      int max_iterations)
+{
+    const int vertices_count = graph.get_vertices_count();
+    VerticesArrayB200<int> number_of_loops(graph), incoming_degrees(graph), incoming_degrees_without_loops(graph);
+    VerticesArrayB200<float> reversed_degrees(graph), old_page_ranks(graph);
+    frontier.set_all_active();
+    graph_API.change_traversal_direction(GATHER);
+    auto get_incoming_degrees = [incoming_degrees] __VGLB_COMPUTE_ARGS__ { incoming_degrees[src_id] = connections_count; };
+    graph_API.compute(graph, frontier, get_incoming_degrees);
+    const float d = 0.85f;
+    const float k = (float)((1.0 - d) / ((float)vertices_count));
+    auto init_data = [page_ranks, number_of_loops, vertices_count] __VGLB_COMPUTE_ARGS__ {
+        page_ranks[src_id] = (float)(1.0 / vertices_count);
+        number_of_loops[src_id] = 0;
+    };
+    graph_API.compute(graph, frontier, init_data);
+    auto calculate_number_of_loops = [number_of_loops] __VGLB_GATHER_ARGS__ {
+        if (src_id == dst_id) atomicAdd(&number_of_loops[src_id], 1);
+    };
+    graph_API.gather(graph, frontier, calculate_number_of_loops);
+    auto calculate_reversed_degrees = [reversed_degrees, incoming_degrees_without_loops, incoming_degrees, number_of_loops] __VGLB_COMPUTE_ARGS__ {
+        const int deg = incoming_degrees[src_id] - number_of_loops[src_id];
+        incoming_degrees_without_loops[src_id] = deg;
+        reversed_degrees[src_id] = deg == 0 ? 0.0f : (float)(1.0 / deg);
+    };
+    graph_API.compute(graph, frontier, calculate_reversed_degrees);
+    graph_API.change_traversal_direction(SCATTER);
+    for (int it = 0; it < max_iterations; it++)
+    {
+        auto save_old_ranks = [old_page_ranks, page_ranks] __VGLB_COMPUTE_ARGS__ {
+            old_page_ranks[src_id] = page_ranks[src_id];
+            page_ranks[src_id] = 0;
+        };
+        graph_API.compute(graph, frontier, save_old_ranks);
+        auto reduce_dangling_input = [incoming_degrees_without_loops, old_page_ranks, vertices_count] __VGLB_REDUCE_FLT_ARGS__ {
+            return incoming_degrees_without_loops[src_id] == 0 ? old_page_ranks[src_id] / vertices_count : 0.0f;
+        };
+        const float dangling_input = graph_API.reduce<float>(graph, frontier, reduce_dangling_input, REDUCE_SUM);
+        auto edge_op = [page_ranks, old_page_ranks, reversed_degrees] __VGLB_SCATTER_ARGS__ {
+            if (src_id != dst_id) atomicAdd(&page_ranks[src_id], old_page_ranks[dst_id] * reversed_degrees[dst_id]);
+        };
+        auto vertex_postprocess_op = [page_ranks, k, d, dangling_input] __VGLB_ADVANCE_POSTPROCESS_ARGS__ {
+            page_ranks[src_id] = k + d * (page_ranks[src_id] + dangling_input);
+        };
+        NoVertexOp EMPTY_VERTEX_OP;
+        graph_API.scatter(graph, frontier, edge_op, EMPTY_VERTEX_OP, vertex_postprocess_op, edge_op, EMPTY_VERTEX_OP, vertex_postprocess_op);
+    }
+}
+
+template <typename T>
+static void dump(const std::string &dir, const char *name, const std::vector<T> &v)
+{
+    const std::string path = dir + "/" + name;
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f || fwrite(v.data(), sizeof(T), v.size(), f) != v.size())
+    {
+        fprintf(stderr, "cannot write %s\n", path.c_str());
+        exit(2);
+    }
+    fclose(f);
+}
+
+int main(int argc, char **argv)
+{
+    if (argc != 9)
+    {
+        fprintf(stderr, "usage: %s kind scale edge_factor seed source_orig weight_seed pr_iters out_dir\n", argv[0]);
+        return 2;
+    }
+    const int kind = atoi(argv[1]), scale = atoi(argv[2]), ef = atoi(argv[3]);
+    const unsigned long long seed = strtoull(argv[4], NULL, 0), weight_seed = strtoull(argv[6], NULL, 0);
+    const int source_orig = atoi(argv[5]), pr_iters = atoi(argv[7]);
+    const std::string out_dir = argv[8];
+    try
+    {
+        const int V = 1 << scale;
+        const long long E = (long long)ef << scale;
+        std::vector<int> src((size_t)E), dst((size_t)E);
+        check(vglb_generate_edges_host(kind, scale, E, seed, 57, 19, 19, src.data(), dst.data()));
+        RuntimeB200 runtime(0);
+        GraphB200 graph(runtime, V, E, src.data(), dst.data());
+        GraphAbstractionsB200 graph_API(graph);
+        FrontierB200 frontier(graph), all_active(graph);
+        const int source_vertex = graph.reorder(source_orig, ORIGINAL, SCATTER);
+
+        VerticesArrayB200<int> levels(graph);
+        const int last_level = bfs_top_down(graph, graph_API, frontier, levels, source_vertex);
+        dump(out_dir, "bfs_levels.bin", levels.to_host_original());
+
+        EdgesArrayB200<float> weights(graph);
+        weights.set_synthetic_weights(weight_seed);
+        VerticesArrayB200<float> distances(graph);
+        const int sssp_rounds = sssp_partial_active(graph, graph_API, frontier, all_active, weights, distances, source_vertex);
+        dump(out_dir, "sssp_dist.bin", distances.to_host_original());
+
+        VerticesArrayB200<int> components(graph);
+        const int cc_rounds = cc_shiloach_vishkin(graph, graph_API, frontier, components);
+        dump(out_dir, "cc_labels.bin", components.to_host_original());
+
+        VerticesArrayB200<float> page_ranks(graph);
+        page_rank(graph, graph_API, frontier, page_ranks, pr_iters);
+        dump(out_dir, "pr_ranks.bin", page_ranks.to_host_original());
+
+        // misuse must throw const char*, like the reference (common/advance.hpp:19-26, modification.hpp:33-36)
+        int caught = 0;
+        auto noop = [] __VGLB_SCATTER_ARGS__ {};
+        try { graph_API.gather(graph, frontier, noop); } catch (const char *) { caught++; }   // SCATTER direction is current
+        frontier.clear();
+        frontier.add_vertex(0);
+        try { frontier.add_vertex(1); } catch (const char *) { caught++; }                     // non-empty frontier
+        // reduce max over a sparse frontier + the frontier's bookkeeping
+        auto deg_op = [] __VGLB_REDUCE_INT_ARGS__ { return connections_count; };
+        frontier.set_all_active();
+        const int max_deg = graph_API.reduce<int>(graph, frontier, deg_op, REDUCE_MAX);
+        const long long deg_sum = (long long)graph_API.reduce<double>(graph, frontier, deg_op, REDUCE_SUM);
+        runtime.synchronize();
+        printf("SHIM_OK V=%d E=%lld bfs_last_level=%d sssp_rounds=%d cc_rounds=%d errors_caught=%d max_degree=%d degree_sum=%lld info_max_degree=%d\n",
+               V, E, last_level, sssp_rounds, cc_rounds, caught, max_deg, deg_sum, graph.info.max_degree);
+    }
+    catch (const char *msg)
+    {
+        fprintf(stderr, "VGL error: %s\n", msg);
+        return 1;
+    }
+    return 0;
+}

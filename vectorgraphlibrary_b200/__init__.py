@@ -103,6 +103,7 @@ _SIGNATURES = {
     "vglb_frontier_add_vertex": (C.c_int, [_P, _P, C.c_int32]),
     "vglb_frontier_get_info": (C.c_int, [_P, _P, C.POINTER(FrontierInfo)]),
     "vglb_gnf_from_flags": (C.c_int, [_P, _P, _P]),
+    "vglb_gnf_from_bitmap": (C.c_int, [_P, _P, _P]),
     "vglb_gnf_eq_i32": (C.c_int, [_P, _P, _P, C.c_int32]),
     "vglb_gnf_ne_u32": (C.c_int, [_P, _P, _P, _P]),
     "vglb_reduce_sum_i32": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int64)]),

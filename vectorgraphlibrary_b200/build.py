@@ -76,9 +76,31 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+SHIM_SRC = os.path.join(ROOT, "tests", "shim", "shim_algorithms.cu")
+SHIM_BIN = os.path.join(ROOT, "tests", "shim", "shim_algorithms")
+
+
+def build_shim_test(force: bool = False) -> str:
+    """The C++ host side above the C ABI: tests/shim/shim_algorithms.cu instantiates the user-lambda operator API
+    (include/vgl_b200/graph_abstractions_b200.cuh) in its own translation unit, exactly as a VGL algorithm source
+    would, and links libvgl_b200.so. Built here so the binary travels to the GPU box with the snapshot."""
+    headers = sorted(glob.glob(os.path.join(ROOT, "include", "*.h")) + glob.glob(os.path.join(ROOT, "include", "vgl_b200", "*")))
+    if force or _stale(SHIM_BIN, [SHIM_SRC, LIB] + headers):
+        cmd = [_nvcc(), "-O2", "-std=c++17", "--extended-lambda", "--expt-relaxed-constexpr", "-gencode",
+               "arch=compute_100a,code=sm_100a", "-lineinfo", "-ccbin", "/usr/bin/g++", "-I", os.path.join(ROOT, "include"),
+               SHIM_SRC, "-L", HERE, "-lvgl_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../vectorgraphlibrary_b200",
+               "-o", SHIM_BIN]
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        if p.returncode != 0:
+            sys.stderr.write(p.stdout + p.stderr)
+            raise RuntimeError("nvcc failed on tests/shim/shim_algorithms.cu")
+    return SHIM_BIN
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     a = ap.parse_args()
     print(build(a.force, a.verbose))
+    print(build_shim_test(a.force))

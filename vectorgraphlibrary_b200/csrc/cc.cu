@@ -136,7 +136,7 @@ static int cc_partitioned(vglb_ctx *ctx, vglb_graph *g, int32_t *d_labels, vglb_
         CUDA_TRY(cudaMemsetAsync(d_changed, 0, sizeof(int), st));
         if (plan.blocks > 0)
         {
-            vglb::advance_all_active_kernel<<<(unsigned)plan.blocks, vglb::kAdvThreads, 0, st>>>(view, plan, 0LL, hook, none, none);
+            vglb::advance_all_active_kernel<<<(unsigned)plan.blocks, vglb::kAdvThreads, 0, st>>>(view, plan, 0LL, hook, none, none, hook, none, none);
             KERNEL_TRY();
             ctx->launches++;
         }
@@ -202,7 +202,7 @@ extern "C" int vglb_cc(vglb_ctx *ctx, vglb_graph *g, int32_t *d_labels, vglb_sta
         CUDA_TRY(cudaMemsetAsync(d_changed, 0, sizeof(int), st));
         if (plan.blocks > 0)
         {
-            vglb::advance_all_active_kernel<<<(unsigned)plan.blocks, vglb::kAdvThreads, 0, st>>>(view, plan, 0LL, hook, none, none);
+            vglb::advance_all_active_kernel<<<(unsigned)plan.blocks, vglb::kAdvThreads, 0, st>>>(view, plan, 0LL, hook, none, none, hook, none, none);
             KERNEL_TRY();
             ctx->launches++;
         }

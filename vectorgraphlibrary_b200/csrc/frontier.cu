@@ -60,6 +60,12 @@ struct PredNeU32
     __device__ __forceinline__ bool operator()(int32_t v) const { return a[v] != b[v]; }
 };
 
+struct PredBitmap
+{
+    const uint32_t *bits;
+    __device__ __forceinline__ bool operator()(int32_t v) const { return (bits[v >> 5] >> (v & 31)) & 1u; }
+};
+
 template <class Pred>
 __global__ void __launch_bounds__(GNF_THREADS)
 gnf_compact_kernel(Pred pred, const int64_t *__restrict__ ptr, int32_t V, int32_t b0, int32_t b1,
@@ -306,6 +312,14 @@ extern "C" int vglb_gnf_from_flags(vglb_ctx *ctx, vglb_frontier *f, const int32_
 {
     VGLB_REQUIRE(ctx != NULL && f != NULL && d_flags != NULL, "vglb_gnf_from_flags: NULL argument");
     PredFlags p{d_flags};
+    return gnf_run(ctx, f, p);
+}
+
+extern "C" int vglb_gnf_from_bitmap(vglb_ctx *ctx, vglb_frontier *f, const uint32_t *d_bits)
+{
+    VGLB_REQUIRE(ctx != NULL && f != NULL && d_bits != NULL, "vglb_gnf_from_bitmap: NULL argument");
+    VGLB_REQUIRE(d_bits != (const uint32_t *)f->d_bitmap, "vglb_gnf_from_bitmap: the input must not be the frontier's own bitmap");
+    PredBitmap p{d_bits};
     return gnf_run(ctx, f, p);
 }
 
