@@ -11,12 +11,14 @@
 // B200 design
 //   * distances of non-negative floats order like their bit patterns: relax = atomicMin on the uint32 view, after a
 //     plain (L2-resident) read that filters the candidates that cannot win;
-//   * the next frontier is emitted inside the advance: the thread that lowers dist[v] marks v in a per-round bitmap
-//     (atomicOr); the first marker enqueues v into the queue of its degree tier. No `prev` copy, no V-pass GNF —
-//     the reference's two full-V passes per round (shortest_paths.hpp:40-44,58-66) disappear;
-//   * same degree-binned queues / CTA-warp-8-lane tiers as bfs.cu; column indices and weights are streamed together
+//   * the winner of an atomicMin marks the vertex in a "due" bitmap, so the next frontier comes from a 2 MB bitmap scan —
+//     the reference's `prev = dist` copy and its V-pass generate_new_frontier (shortest_paths.hpp:40-44,58-66) disappear;
+//   * near/far schedule (see vglb_sssp): only due vertices below a moving distance threshold are relaxed, which cuts
+//     the edges relaxed on the BASELINE graph from 5.8 E (the reference's schedule) to ~1.2 E with bit-identical results;
+//   * load balance: a warp takes up to 32 queued rows and walks the concatenation of their edge ranges (shuffle search
+//     over the prefix sums), rows with >= 4096 edges get a CTA; column indices and weights are streamed
 //     (ld.global.nc.L1::no_allocate + L2 evict-first), the distance vector is the L2-resident gather target.
-// HBM roofline: algorithmic bytes = sum_rounds [ 12 e_i (index + weight + dist[dst]) + 24 f_i + 8 n(F_{i+1}) ].
+// HBM roofline: algorithmic bytes = sum_rounds [ 12 e_i (index + weight + dist[dst]) + 24 f_i + 8 n(F_{i+1}) ] + scans.
 #include <float.h>
 #include <stdlib.h>
 
@@ -26,46 +28,26 @@
 #define SSSP_THREADS 256
 #define SSSP_SMALL_LANES 8
 
-// PART = one rank's part of a partitioned graph: `dist` is the replicated vector (column ids), winners are not queued
-// here — owners find their changed vertices after the allreduce(min).
-template <int NT, bool PART>
+// Row-per-group relax used by the partitioned driver: NT threads (a CTA, a warp or an 8-lane group) stride the out-row
+// [s,e) of one frontier vertex and lower the distances in this rank's replica of the vector (column ids); owners find
+// their changed vertices after the allreduce(min).
+template <int NT>
 __device__ __forceinline__ void sssp_expand(const int32_t *__restrict__ adj, const float *__restrict__ wgt, int64_t s,
-                                            int64_t e, int tid, float du, uint32_t *__restrict__ dist,
-                                            uint32_t *__restrict__ mark, int32_t b0, int32_t b1, const TierQueues &nq,
-                                            unsigned long long *counters, uint64_t pol_stream)
+                                            int64_t e, int tid, float du, uint32_t *__restrict__ dist, uint64_t pol_stream)
 {
-    for (int64_t p = s + tid;; p += NT)
+    for (int64_t p = s + tid; p < e; p += NT)
     {
-        const bool active = p < e;
-        if (!__any_sync(0xffffffffu, active)) break;
-        bool won = false;
-        int32_t v = 0;
-        if (active)
-        {
-            v = ld_stream_s32(adj + p, pol_stream);
-            const float w = ld_stream_f32(wgt + p, pol_stream);
-            const uint32_t cand = __float_as_uint(__fadd_rn(du, w)); // shortest_paths.hpp:50-53
-            if (cand < dist[v])
-            {
-                const uint32_t old = atomicMin(&dist[v], cand);
-                if (!PART && cand < old)
-                {
-                    const uint32_t bit = 1u << (v & 31);
-                    const uint32_t m = atomicOr(&mark[v >> 5], bit);
-                    won = !(m & bit);
-                }
-            }
-        }
-        if (!PART) enqueue_binned(won, v, b0, b1, nq, counters);
+        const int32_t v = ld_stream_s32(adj + p, pol_stream);
+        const float w = ld_stream_f32(wgt + p, pol_stream);
+        const uint32_t cand = __float_as_uint(__fadd_rn(du, w)); // shortest_paths.hpp:50-53
+        if (cand < dist[v]) atomicMin(&dist[v], cand);
     }
 }
 
-template <bool PART>
 __global__ void __launch_bounds__(SSSP_THREADS)
-sssp_relax_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, const float *__restrict__ wgt,
-                  TierQueues cq, int32_t n_big, int32_t n_mid, int32_t n_small, int32_t blocks_mid, int32_t blocks_small,
-                  uint32_t *__restrict__ dist, uint32_t *__restrict__ mark, int32_t b0, int32_t b1, TierQueues nq,
-                  unsigned long long *counters, int32_t col0)
+sssp_relax_rows_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, const float *__restrict__ wgt,
+                       TierQueues cq, int32_t n_big, int32_t n_mid, int32_t n_small, int32_t blocks_mid, int32_t blocks_small,
+                       uint32_t *__restrict__ dist, unsigned long long *counters, int32_t col0)
 {
     const uint64_t pol = l2_policy_evict_first();
     const int b = blockIdx.x;
@@ -77,7 +59,7 @@ sssp_relax_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ a
         const int64_t s = ptr[u], e = ptr[u + 1];
         const float du = __uint_as_float(dist[col0 + u]);
         if (threadIdx.x == 0) edges = e - s;
-        sssp_expand<SSSP_THREADS, PART>(adj, wgt, s, e, threadIdx.x, du, dist, mark, b0, b1, nq, counters, pol);
+        sssp_expand<SSSP_THREADS>(adj, wgt, s, e, threadIdx.x, du, dist, pol);
     }
     else if (b < n_big + blocks_mid)
     {
@@ -88,7 +70,7 @@ sssp_relax_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ a
             const int64_t s = ptr[u], e = ptr[u + 1];
             const float du = __uint_as_float(dist[col0 + u]);
             if (lane == 0) edges += e - s;
-            sssp_expand<32, PART>(adj, wgt, s, e, lane, du, dist, mark, b0, b1, nq, counters, pol);
+            sssp_expand<32>(adj, wgt, s, e, lane, du, dist, pol);
         }
     }
     else
@@ -97,26 +79,18 @@ sssp_relax_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ a
         constexpr int GROUPS = SSSP_THREADS / G;
         const int ngroups = blocks_small * GROUPS;
         const int gid = threadIdx.x / G, gl = threadIdx.x % G;
-        for (int base = (b - n_big - blocks_mid) * GROUPS; base < n_small; base += ngroups)
+        for (int i = (b - n_big - blocks_mid) * GROUPS + gid; i < n_small; i += ngroups)
         {
-            const int i = base + gid;
-            int64_t s = 0, e = 0;
-            float du = 0.f;
-            if (i < n_small)
-            {
-                const int32_t u = cq.q[2][i];
-                s = ptr[u];
-                e = ptr[u + 1];
-                du = __uint_as_float(dist[col0 + u]);
-                if (gl == 0) edges += e - s;
-            }
-            sssp_expand<G, PART>(adj, wgt, s, e, gl, du, dist, mark, b0, b1, nq, counters, pol);
+            const int32_t u = cq.q[2][i];
+            const int64_t s = ptr[u], e = ptr[u + 1];
+            const float du = __uint_as_float(dist[col0 + u]);
+            if (gl == 0) edges += e - s;
+            sssp_expand<G>(adj, wgt, s, e, gl, du, dist, pol);
         }
     }
     edges = warp_sum_i64(edges);
     if (lane == 0 && edges) atomicAdd(&counters[C_EDGES], (unsigned long long)edges);
 }
-
 
 // ---- 1D-partitioned SSSP ---------------------------------------------------------------------------------------------
 // Each rank relaxes the out-edges of the frontier vertices it owns into its replica of the distance vector (atomicMin),
@@ -210,8 +184,8 @@ static int sssp_partitioned(vglb_ctx *ctx, vglb_graph *g, const float *d_weights
         const int64_t grid = (int64_t)n[0] + blocks_mid + blocks_small;
         if (grid > 0)
         {
-            sssp_relax_kernel<true><<<(unsigned)grid, SSSP_THREADS, 0, st>>>(g->d_out_ptr, g->d_out_adj, d_weights, cq, n[0], n[1], n[2],
-                                                                            blocks_mid, blocks_small, dist, NULL, b0, b1, nq, d_cnt, col0);
+            sssp_relax_rows_kernel<<<(unsigned)grid, SSSP_THREADS, 0, st>>>(g->d_out_ptr, g->d_out_adj, d_weights, cq, n[0], n[1], n[2],
+                                                                           blocks_mid, blocks_small, dist, d_cnt, col0);
             KERNEL_TRY();
             ctx->launches++;
         }
@@ -261,6 +235,126 @@ static int sssp_partitioned(vglb_ctx *ctx, vglb_graph *g, const float *d_weights
     return VGLB_OK;
 }
 
+
+// ---- load-balanced relax of the queued rows with < 4096 edges ("warp-level merge path") -------------------------------
+// A warp takes 32 queue entries; lane j holds row j's edge range and source distance. The 32 ranges are concatenated
+// (warp prefix sum of the degrees) and the warp walks the concatenation 32 * SSSP_FLAT_UNROLL edges at a time: every lane
+// finds the row of its edge with a 5-step shuffle search over the prefix, so all lanes carry an edge whatever the degree
+// mix, loads of one row are consecutive (the queue is ascending, so neighbouring rows are neighbours in memory too),
+// and SSSP_FLAT_UNROLL independent index/weight loads are in flight per lane before the dependent distance gathers.
+#define SSSP_FLAT_UNROLL 4
+
+// relax one edge: atomicMin on the uint32 view after a plain read that filters the losers; the winner marks the vertex
+// as due in the near (new distance below the threshold) or the far bitmap
+__device__ __forceinline__ void sssp_relax_one(uint32_t *__restrict__ dist, uint32_t *__restrict__ near_bm,
+                                               uint32_t *__restrict__ far_bm, uint32_t threshold_bits, int32_t v, uint32_t c)
+{
+    if (c < dist[v])
+    {
+        const uint32_t old = atomicMin(&dist[v], c);
+        if (c < old)
+        {
+            uint32_t *bm = c < threshold_bits ? near_bm : far_bm;
+            const uint32_t bit = 1u << (v & 31);
+            if (!(bm[v >> 5] & bit)) atomicOr(&bm[v >> 5], bit);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SSSP_THREADS)
+sssp_relax_flat_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, const float *__restrict__ wgt,
+                       TierQueues cq, int32_t n_big, int32_t n_mid, int32_t n_small, int32_t per_warp,
+                       uint32_t *__restrict__ dist, uint32_t *__restrict__ near_bm, uint32_t *__restrict__ far_bm,
+                       uint32_t threshold_bits, unsigned long long *counters)
+{
+    const unsigned FULL = 0xffffffffu;
+    const uint64_t pol = l2_policy_evict_first();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long edges = 0;
+    if ((int)blockIdx.x < n_big)
+    {
+        // a row with >= 4096 edges: the whole CTA strides it
+        const int32_t u = cq.q[0][blockIdx.x];
+        const int64_t s = ptr[u], e = ptr[u + 1];
+        const float du = __uint_as_float(dist[u]);
+        if (threadIdx.x == 0) edges = e - s;
+        for (int64_t p = s + threadIdx.x; p < e; p += SSSP_THREADS)
+        {
+            const int32_t v = ld_stream_s32(adj + p, pol);
+            const uint32_t c = __float_as_uint(__fadd_rn(du, ld_stream_f32(wgt + p, pol)));
+            sssp_relax_one(dist, near_bm, far_bm, threshold_bits, v, c);
+        }
+    }
+    else
+    {
+        // per_warp (a power of two <= 32) queue entries per warp: small frontiers are spread over more warps
+        const int batches_mid = (n_mid + per_warp - 1) / per_warp, batches_small = (n_small + per_warp - 1) / per_warp;
+        const int batch = ((int)blockIdx.x - n_big) * (SSSP_THREADS / 32) + warp;
+        if (batch < batches_mid + batches_small)
+        {
+            const bool mid = batch < batches_mid;
+            const int32_t *q = mid ? cq.q[1] : cq.q[2];
+            const int n = mid ? n_mid : n_small;
+            const int i = (mid ? batch : batch - batches_mid) * per_warp + lane;
+            int64_t s = 0;
+            int deg = 0;
+            float du = 0.f;
+            if (lane < per_warp && i < n)
+            {
+                const int32_t u = q[i];
+                s = ptr[u];
+                deg = (int)(ptr[u + 1] - s);
+                du = __uint_as_float(dist[u]);
+            }
+            int incl = deg;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const int t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int excl = incl - deg;
+            const int total = __shfl_sync(FULL, incl, 31);
+            if (lane == 0) edges = total;
+            for (int base = 0; base < total; base += 32 * SSSP_FLAT_UNROLL)
+            {
+                int32_t v[SSSP_FLAT_UNROLL];
+                float cand[SSSP_FLAT_UNROLL];
+#pragma unroll
+                for (int k = 0; k < SSSP_FLAT_UNROLL; k++)
+                {
+                    const int idx = base + k * 32 + lane;
+                    int j = 0; // largest lane whose range starts at or before idx
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1)
+                    {
+                        const int ex = __shfl_sync(FULL, excl, j + step);
+                        if (ex <= idx) j += step;
+                    }
+                    const int64_t sj = __shfl_sync(FULL, s, j);
+                    const int exj = __shfl_sync(FULL, excl, j);
+                    const float duj = __shfl_sync(FULL, du, j);
+                    v[k] = -1;
+                    cand[k] = 0.f;
+                    if (idx < total)
+                    {
+                        const int64_t p = sj + (idx - exj);
+                        v[k] = ld_stream_s32(adj + p, pol);
+                        cand[k] = __fadd_rn(duj, ld_stream_f32(wgt + p, pol)); // shortest_paths.hpp:50-53
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < SSSP_FLAT_UNROLL; k++)
+                {
+                    if (v[k] >= 0) sssp_relax_one(dist, near_bm, far_bm, threshold_bits, v[k], __float_as_uint(cand[k]));
+                }
+            }
+        }
+    }
+    edges = warp_sum_i64(edges);
+    if (lane == 0 && edges) atomicAdd(&counters[C_EDGES], (unsigned long long)edges);
+}
+
 __global__ void sssp_init_kernel(uint32_t *__restrict__ dist, int32_t V, int32_t source, int32_t *queue_slot)
 {
     const uint32_t inf_bits = __float_as_uint(FLT_MAX - 100.0f); // shortest_paths.hpp:22
@@ -269,6 +363,128 @@ __global__ void sssp_init_kernel(uint32_t *__restrict__ dist, int32_t V, int32_t
     if (blockIdx.x == 0 && threadIdx.x == 0) *queue_slot = source;
 }
 
+// frontier selection of one round (generate_new_frontier, shortest_paths.hpp:58-66) from the due bitmaps: one thread
+// per 32-vertex word. FAR = false: every bit of the near bitmap is due and below the threshold — the word is taken and
+// cleared (and the same bits are cleared in the far bitmap: the vertex is being relaxed with a smaller distance).
+// FAR = true (the near bitmap ran dry, the threshold moved): bits of the far bitmap whose distance is now below the
+// threshold are taken, the rest are counted as pending and their minimum distance recorded. Queue slots are claimed
+// once per CTA and degree tier.
+template <bool FAR>
+__global__ void __launch_bounds__(256)
+sssp_select_kernel(uint32_t *__restrict__ near_bm, uint32_t *__restrict__ far_bm, const uint32_t *__restrict__ dist, int32_t rows,
+                   uint32_t threshold_bits, int32_t b0, int32_t b1, TierQueues nq, unsigned long long *counters)
+{
+    __shared__ int s_count[8][3];
+    __shared__ unsigned long long s_base[3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int32_t nwords = (rows + 31) >> 5;
+    const int32_t w = blockIdx.x * 256 + threadIdx.x;
+    uint32_t take = 0;
+    int pending = 0;
+    uint32_t min_pending = 0xffffffffu;
+    if (w < nwords)
+    {
+        if (!FAR)
+        {
+            take = near_bm[w];
+            if (take)
+            {
+                near_bm[w] = 0;
+                const uint32_t f = far_bm[w];
+                if (f & take) far_bm[w] = f & ~take;
+            }
+        }
+        else
+        {
+            uint32_t bits = far_bm[w];
+            const uint32_t all = bits;
+            while (bits)
+            {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const uint32_t d = dist[(w << 5) + b];
+                if (d < threshold_bits) take |= 1u << b;
+                else
+                {
+                    pending++;
+                    min_pending = min(min_pending, d);
+                }
+            }
+            if (take) far_bm[w] = all & ~take;
+        }
+    }
+    const int32_t base = w << 5;
+    const uint32_t m0 = below_border_mask(base, b0), m1 = below_border_mask(base, b1);
+    uint32_t part[3] = {take & m0, take & m1 & ~m0, take & ~m1};
+    int incl[3];
+#pragma unroll
+    for (int t = 0; t < 3; t++)
+    {
+        int x = __popc(part[t]);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        incl[t] = x;
+        if (lane == 31) s_count[warp][t] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3)
+    {
+        int total = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) total += s_count[i][threadIdx.x];
+        s_base[threadIdx.x] = total ? atomicAdd(&counters[C_NEXT_BIG + threadIdx.x], (unsigned long long)total) : 0ULL;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < 3; t++)
+    {
+        if (!part[t]) continue;
+        unsigned long long pos = s_base[t] + incl[t] - __popc(part[t]);
+        for (int i = 0; i < warp; i++) pos += s_count[i][t];
+        uint32_t bits = part[t];
+        while (bits)
+        {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            nq.q[t][pos++] = base + b;
+        }
+    }
+    if (FAR)
+    {
+        pending = (int)warp_sum_i64(pending);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) min_pending = min(min_pending, __shfl_xor_sync(0xffffffffu, min_pending, o));
+        if (lane == 0 && pending)
+        {
+            atomicAdd(&counters[C_FOUND], (unsigned long long)pending);
+            atomicMax(&counters[C_MF], (unsigned long long)(0xffffffffu - min_pending)); // min as max of the complement
+        }
+    }
+}
+
+__global__ void sssp_seed_kernel(uint32_t *near_bm, int32_t source) { near_bm[source >> 5] = 1u << (source & 31); }
+
+// largest weight among a sample of the edge array (threshold step of the near/far split)
+__global__ void sssp_weight_sample_kernel(const float *__restrict__ w, int64_t E, int64_t stride, unsigned int *out)
+{
+    float m = 0.f;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * stride; i < E; i += (int64_t)gridDim.x * blockDim.x * stride)
+        m = fmaxf(m, w[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
+// Schedule. The reference relaxes the out-edges of EVERY vertex whose distance changed in the previous round
+// (shortest_paths.hpp:40-66); on the BASELINE graph that re-relaxes each edge ~5.6 times. The fixed point
+// does not depend on the schedule, so the frontier is split near/far: only due vertices with dist < threshold are
+// relaxed; when none is left the threshold moves to (smallest pending distance + delta). delta = sampled max weight *
+// VGLB_SSSP_DELTA_SCALE / average degree (default scale 4; 0 or a huge value = the reference's plain schedule).
+// Distances stay bit-exact (same min-plus fixed point); edges_inspected reports the edges actually relaxed.
 extern "C" int vglb_sssp(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, int32_t source, float *d_dist,
                          vglb_stats *stats)
 {
@@ -277,62 +493,109 @@ extern "C" int vglb_sssp(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, i
     if (g->comm) return sssp_partitioned(ctx, g, d_weights, source, d_dist, stats);
     VGLB_REQUIRE(source >= 0 && source < g->V, "vglb_sssp: source out of range");
     CUDA_TRY(cudaSetDevice(ctx->device));
-    const size_t words = ((size_t)g->V + 31) / 32;
     if (!g->d_queue[0])
     {
         CUDA_TRY(cudaMalloc(&g->d_queue[0], ((size_t)g->V + 3) * 4));
         CUDA_TRY(cudaMalloc(&g->d_queue[1], ((size_t)g->V + 3) * 4));
     }
+    const size_t words = ((size_t)g->V + 31) / 32;
     if (!g->d_visited) CUDA_TRY(cudaMalloc(&g->d_visited, (words + 32) * 4));
+    if (!g->d_front_bm[0]) CUDA_TRY(cudaMalloc(&g->d_front_bm[0], (words + 32) * 4));
     const int64_t launches0 = ctx->launches;
     const int32_t V = g->V, b0 = g->tier_border[0], b1 = g->tier_border[1];
     unsigned long long *d_cnt = (unsigned long long *)ctx->d_counters;
     unsigned long long *h_cnt = (unsigned long long *)ctx->h_counters;
     cudaStream_t st = ctx->stream;
-    uint32_t *dist = (uint32_t *)d_dist, *mark = g->d_visited;
-    auto regions = [&](int32_t *base) {
-        TierQueues q;
-        q.q[0] = base;
-        q.q[1] = base + b0;
-        q.q[2] = base + b1;
-        return q;
-    };
-    TierQueues cq = regions(g->d_queue[0]), nq = regions(g->d_queue[1]);
+    uint32_t *dist = (uint32_t *)d_dist, *near_bm = g->d_visited, *far_bm = g->d_front_bm[0];
+    TierQueues cq;
+    cq.q[0] = g->d_queue[0];
+    cq.q[1] = g->d_queue[0] + b0;
+    cq.q[2] = g->d_queue[0] + b1;
 
     CUDA_TRY(cudaEventRecord(ctx->ev_start, st));
-    const int src_tier = source < b0 ? 0 : (source < b1 ? 1 : 2);
-    sssp_init_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(dist, V, source, cq.q[src_tier]);
-    KERNEL_TRY();
-    ctx->launches++;
-    CUDA_TRY(cudaMemsetAsync(d_cnt, 0, C_COUNT * 8, st));
-    int32_t n[3] = {0, 0, 0};
-    n[src_tier] = 1;
-    long long n_cur = 1;
-    int64_t tot_edges = 0, tot_rows = 0, tot_next = 0, rounds = 0;
-    const int max_blocks = ctx->sm_count * 16;
-    while (n_cur > 0)
+    // threshold step
+    double scale = 4.0;
+    if (const char *e = getenv("VGLB_SSSP_DELTA_SCALE")) scale = atof(e);
+    float delta = 0.f; // 0 = plain schedule
+    if (scale > 0.0 && g->E > 0)
     {
-        CUDA_TRY(cudaMemsetAsync(mark, 0, words * 4, st));
-        const int blocks_mid = (int)min((int64_t)max_blocks, ceil_div64(n[1], SSSP_THREADS / 32));
-        const int blocks_small = (int)min((int64_t)max_blocks, ceil_div64(n[2], SSSP_THREADS / SSSP_SMALL_LANES));
-        const int64_t grid = (int64_t)n[0] + blocks_mid + blocks_small;
-        sssp_relax_kernel<false><<<(unsigned)grid, SSSP_THREADS, 0, st>>>(g->d_out_ptr, g->d_out_adj, d_weights, cq, n[0], n[1],
-                                                                         n[2], blocks_mid, blocks_small, dist, mark, b0, b1, nq,
-                                                                         d_cnt, 0);
+        unsigned int *d_max = (unsigned int *)(d_cnt + 60);
+        CUDA_TRY(cudaMemsetAsync(d_max, 0, 4, st));
+        const int64_t stride = g->E > (1 << 22) ? g->E >> 22 : 1;
+        sssp_weight_sample_kernel<<<64, 256, 0, st>>>(d_weights, g->E, stride, d_max);
         KERNEL_TRY();
         ctx->launches++;
+        unsigned int bits = 0;
+        CUDA_TRY(cudaMemcpyAsync(&bits, d_max, 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        float wmax;
+        memcpy(&wmax, &bits, 4);
+        const double avg_deg = (double)g->E / (double)V;
+        delta = (float)(scale * (double)wmax / (avg_deg > 1.0 ? avg_deg : 1.0));
+    }
+    const bool trace = getenv("VGLB_SSSP_TRACE") != NULL; // developer aid: one line per selection on stderr
+    const float inf = FLT_MAX - 100.0f;
+    const bool split = delta > 0.f && delta < inf;
+    float threshold = split ? delta : inf;
+    sssp_init_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(dist, V, source, cq.q[0]);
+    KERNEL_TRY();
+    CUDA_TRY(cudaMemsetAsync(near_bm, 0, words * 4, st));
+    CUDA_TRY(cudaMemsetAsync(far_bm, 0, words * 4, st));
+    sssp_seed_kernel<<<1, 1, 0, st>>>(near_bm, source);
+    KERNEL_TRY();
+    CUDA_TRY(cudaMemsetAsync(d_cnt, 0, C_COUNT * 8, st));
+    ctx->launches += 2;
+    int64_t tot_edges = 0, tot_rows = 0, tot_next = 0, rounds = 0, selects = 0, far_selects = 0;
+    const unsigned select_grid = (unsigned)ceil_div64((int64_t)words, 256);
+    bool from_far = false;
+    for (;;)
+    {
+        uint32_t tbits;
+        if (threshold >= inf) tbits = 0xffffffffu; // everything that is due
+        else memcpy(&tbits, &threshold, 4);
+        if (from_far) sssp_select_kernel<true><<<select_grid, 256, 0, st>>>(near_bm, far_bm, dist, V, tbits, b0, b1, cq, d_cnt);
+        else sssp_select_kernel<false><<<select_grid, 256, 0, st>>>(near_bm, far_bm, dist, V, tbits, b0, b1, cq, d_cnt);
+        KERNEL_TRY();
+        ctx->launches++;
+        selects++;
+        far_selects += from_far;
         CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, C_COUNT * 8, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         CUDA_TRY(cudaMemsetAsync(d_cnt, 0, C_COUNT * 8, st));
+        const int32_t n[3] = {(int32_t)h_cnt[C_NEXT_BIG], (int32_t)h_cnt[C_NEXT_MID], (int32_t)h_cnt[C_NEXT_SMALL]};
+        const long long n_cur = (long long)n[0] + n[1] + n[2], pending = (long long)h_cnt[C_FOUND];
+        tot_edges += (int64_t)h_cnt[C_EDGES]; // relaxed by the previous round
+        if (trace) fprintf(stderr, "sssp select %lld (%s): threshold %.3f queued %lld pending %lld, previous round relaxed %lld edges\n",
+                           (long long)selects, from_far ? "far" : "near", threshold, n_cur, pending, (long long)h_cnt[C_EDGES]);
+        if (n_cur == 0)
+        {
+            if (!from_far)
+            {
+                if (!split) break;      // plain schedule: nothing is ever parked in the far bitmap
+                from_far = true;        // near ran dry: move the threshold and look at the far bitmap
+                threshold += delta;
+                continue;
+            }
+            if (pending == 0) break;
+            const uint32_t min_bits = 0xffffffffu - (uint32_t)h_cnt[C_MF];
+            float min_pending;
+            memcpy(&min_pending, &min_bits, 4);
+            threshold = fmaxf(threshold, min_pending) + delta; // nothing below the moved threshold: jump
+            continue;
+        }
+        from_far = false;
+        // queue entries per warp: 32 when the frontier is large, fewer when it would leave SMs idle
+        int per_warp = 32;
+        while (per_warp > 1 && ceil_div64(n[1] + n[2], per_warp) < (int64_t)ctx->sm_count * 32) per_warp >>= 1;
+        const int64_t batches = ceil_div64(n[1], per_warp) + ceil_div64(n[2], per_warp);
+        const int64_t grid = (int64_t)n[0] + ceil_div64(batches, SSSP_THREADS / 32);
+        sssp_relax_flat_kernel<<<(unsigned)grid, SSSP_THREADS, 0, st>>>(g->d_out_ptr, g->d_out_adj, d_weights, cq, n[0], n[1], n[2], per_warp,
+                                                                       dist, near_bm, far_bm, tbits, d_cnt);
+        KERNEL_TRY();
+        ctx->launches++;
         rounds++;
         tot_rows += n_cur;
-        tot_edges += (int64_t)h_cnt[C_EDGES];
-        n[0] = (int32_t)h_cnt[C_NEXT_BIG];
-        n[1] = (int32_t)h_cnt[C_NEXT_MID];
-        n[2] = (int32_t)h_cnt[C_NEXT_SMALL];
-        n_cur = (long long)n[0] + n[1] + n[2];
         tot_next += n_cur;
-        TierQueues t = cq; cq = nq; nq = t;
     }
     CUDA_TRY(cudaEventRecord(ctx->ev_stop, st));
     CUDA_TRY(cudaEventSynchronize(ctx->ev_stop));
@@ -345,8 +608,8 @@ extern "C" int vglb_sssp(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, i
         stats->iterations = rounds;
         stats->edges_inspected = tot_edges;
         stats->vertices_processed = tot_rows;
-        stats->frontier_bytes = 8 * tot_next;
-        stats->algorithmic_bytes = 12 * tot_edges + 24 * tot_rows + 8 * tot_next;
+        stats->frontier_bytes = 8 * tot_next + selects * (int64_t)words * 4 + far_selects * 4 * (int64_t)V; // queues, bitmap scans, far-pile distance reads
+        stats->algorithmic_bytes = 12 * tot_edges + 24 * tot_rows + stats->frontier_bytes;
         stats->kernel_launches = ctx->launches - launches0;
     }
     return VGLB_OK;
