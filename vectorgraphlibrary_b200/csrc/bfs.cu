@@ -24,74 +24,136 @@
 #include "common.cuh"
 #include "frontier.cuh"
 
+#include <time.h>
+static double trace_now()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
 #define BFS_THREADS 256
 #define BFS_SMALL_LANES 8
-#define BFS_BU_PROBE 4
+#define BFS_BU_PROBE 4       // in-neighbours probed per batch by one lane
+#define BFS_BU_PROBE_MAX 16  // lane-private probes before the warp takes the row over
+#define BFS_BIG_CHUNK 8192 // a row with >= 4096 edges is expanded by one CTA per chunk of this many edges
 
 // NT threads (a CTA, a warp or an 8-lane group) expand the out-row [s,e) of one frontier vertex.
 // Every thread of the warp must call this together (ballots inside); `e <= s` for idle groups.
 // PART = the graph is one rank's part: `visited` is the replicated bitmap (read only here) and discoveries are only
 // marked in the candidate bitmap `levels` points to (reinterpreted) — owners resolve them after the exchange.
-template <int NT, bool PART>
-__device__ __forceinline__ void td_expand(const int32_t *__restrict__ adj, int64_t s, int64_t e, int tid,
-                                          uint32_t *__restrict__ visited, int32_t *__restrict__ levels, int32_t next_level,
-                                          int32_t b0, int32_t b1, const TierQueues &nq, unsigned long long *counters)
+#define BFS_TD_UNROLL 4 // edges per thread and step: their loads, visited tests and atomics are independent
+
+// one warp-aggregated queue claim per degree tier for BFS_TD_UNROLL candidates per lane
+__device__ __forceinline__ void enqueue_binned_multi(const bool (&won)[BFS_TD_UNROLL], const int32_t (&v)[BFS_TD_UNROLL], int32_t b0,
+                                                     int32_t b1, const TierQueues &nq, unsigned long long *counters)
 {
-    for (int64_t p = s + tid;; p += NT)
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned below = (1u << lane) - 1u;
+#pragma unroll
+    for (int t = 0; t < 3; t++)
     {
-        const bool active = p < e;
-        if (!__any_sync(0xffffffffu, active)) break;
-        bool won = false;
-        int32_t v = 0;
-        if (active)
+        unsigned mask[BFS_TD_UNROLL];
+        int total = 0;
+#pragma unroll
+        for (int k = 0; k < BFS_TD_UNROLL; k++)
         {
-            v = adj[p];
-            const uint32_t bit = 1u << (v & 31);
+            const int tier = v[k] < b0 ? 0 : (v[k] < b1 ? 1 : 2);
+            mask[k] = __ballot_sync(0xffffffffu, won[k] && tier == t);
+            total += __popc(mask[k]);
+        }
+        if (total == 0) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&counters[C_NEXT_BIG + t], (unsigned long long)total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+        for (int k = 0; k < BFS_TD_UNROLL; k++)
+        {
+            if ((mask[k] >> lane) & 1u) nq.q[t][base + __popc(mask[k] & below)] = v[k];
+            base += __popc(mask[k]);
+        }
+    }
+}
+
+template <int NT, bool PART>
+__device__ __forceinline__ void td_expand(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, int64_t s, int64_t e, int tid,
+                                          uint32_t *__restrict__ visited, int32_t *__restrict__ levels, int32_t next_level,
+                                          int32_t b0, int32_t b1, const TierQueues &nq, unsigned long long *counters, long long &mf)
+{
+    for (int64_t p0 = s + tid;; p0 += NT * BFS_TD_UNROLL)
+    {
+        if (!__any_sync(0xffffffffu, p0 < e)) break;
+        bool won[BFS_TD_UNROLL];
+        int32_t v[BFS_TD_UNROLL];
+#pragma unroll
+        for (int k = 0; k < BFS_TD_UNROLL; k++)
+        {
+            const int64_t p = p0 + (int64_t)k * NT;
+            v[k] = p < e ? adj[p] : -1;
+            won[k] = false;
+        }
+        uint32_t seen[BFS_TD_UNROLL];
+#pragma unroll
+        for (int k = 0; k < BFS_TD_UNROLL; k++) seen[k] = v[k] >= 0 ? visited[v[k] >> 5] : 0xffffffffu;
+#pragma unroll
+        for (int k = 0; k < BFS_TD_UNROLL; k++)
+        {
+            if (v[k] < 0) continue;
+            const uint32_t bit = 1u << (v[k] & 31);
+            if (seen[k] & bit) continue;
             if (PART)
             {
                 uint32_t *cand = reinterpret_cast<uint32_t *>(levels);
-                if (!(visited[v >> 5] & bit) && !(cand[v >> 5] & bit)) atomicOr(&cand[v >> 5], bit);
+                if (!(cand[v[k] >> 5] & bit)) atomicOr(&cand[v[k] >> 5], bit);
             }
             else
             {
-                if (!(visited[v >> 5] & bit))
-                {
-                    const uint32_t old = atomicOr(&visited[v >> 5], bit);
-                    won = !(old & bit);
-                }
-                if (won) levels[v] = next_level;
+                const uint32_t old = atomicOr(&visited[v[k] >> 5], bit);
+                won[k] = !(old & bit);
             }
         }
-        if (!PART) enqueue_binned(won, v, b0, b1, nq, counters);
+        if (!PART)
+        {
+#pragma unroll
+            for (int k = 0; k < BFS_TD_UNROLL; k++)
+                if (won[k])
+                {
+                    levels[v[k]] = next_level;
+                    mf += ptr[v[k] + 1] - ptr[v[k]]; // out-degree of the new frontier (m_f of the direction heuristic)
+                }
+            enqueue_binned_multi(won, v, b0, b1, nq, counters);
+        }
     }
 }
 
 template <bool PART>
 __global__ void __launch_bounds__(BFS_THREADS)
-bfs_td_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, TierQueues cq, int32_t n_big, int32_t n_mid,
-              int32_t n_small, int32_t blocks_mid, int32_t blocks_small, uint32_t *__restrict__ visited,
+bfs_td_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, TierQueues cq, int32_t n_big, int32_t big_chunks,
+              int32_t n_mid, int32_t n_small, int32_t blocks_mid, int32_t blocks_small, uint32_t *__restrict__ visited,
               int32_t *__restrict__ levels, int32_t next_level, int32_t b0, int32_t b1, TierQueues nq,
               unsigned long long *counters)
 {
     const int b = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    long long edges = 0;
-    if (b < n_big)
+    long long edges = 0, mf = 0;
+    // hubs: one CTA per BFS_BIG_CHUNK edges of the row (the largest rows of a scale-26 Kronecker graph have > 10^6 edges)
+    const int big_blocks = n_big * big_chunks;
+    if (b < big_blocks)
     {
-        const int32_t u = cq.q[0][b];
-        const int64_t s = ptr[u], e = ptr[u + 1];
-        if (threadIdx.x == 0) edges = e - s;
-        td_expand<BFS_THREADS, PART>(adj, s, e, threadIdx.x, visited, levels, next_level, b0, b1, nq, counters);
+        const int32_t u = cq.q[0][b / big_chunks];
+        const int64_t s = ptr[u] + (int64_t)(b % big_chunks) * BFS_BIG_CHUNK, e = min(ptr[u + 1], s + BFS_BIG_CHUNK);
+        if (threadIdx.x == 0) edges = max(e - s, (int64_t)0);
+        td_expand<BFS_THREADS, PART>(ptr, adj, s, e, threadIdx.x, visited, levels, next_level, b0, b1, nq, counters, mf);
     }
-    else if (b < n_big + blocks_mid)
+    else if (b < big_blocks + blocks_mid)
     {
         const int nwarps = blocks_mid * (BFS_THREADS / 32);
-        for (int i = (b - n_big) * (BFS_THREADS / 32) + warp; i < n_mid; i += nwarps)
+        for (int i = (b - big_blocks) * (BFS_THREADS / 32) + warp; i < n_mid; i += nwarps)
         {
             const int32_t u = cq.q[1][i];
             const int64_t s = ptr[u], e = ptr[u + 1];
             if (lane == 0) edges += e - s;
-            td_expand<32, PART>(adj, s, e, lane, visited, levels, next_level, b0, b1, nq, counters);
+            td_expand<32, PART>(ptr, adj, s, e, lane, visited, levels, next_level, b0, b1, nq, counters, mf);
         }
     }
     else
@@ -101,7 +163,7 @@ bfs_td_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, 
         const int ngroups = blocks_small * GROUPS;
         const int gid = threadIdx.x / G, gl = threadIdx.x % G;
         // all groups of a warp iterate together (ballots in td_expand): pad the trip count to a multiple of the stride
-        const int first = (b - n_big - blocks_mid) * GROUPS + gid;
+        const int first = (b - big_blocks - blocks_mid) * GROUPS + gid;
         for (int base = first - gid; base < n_small; base += ngroups)
         {
             const int i = base + gid;
@@ -113,113 +175,183 @@ bfs_td_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, 
                 e = ptr[u + 1];
                 if (gl == 0) edges += e - s;
             }
-            td_expand<G, PART>(adj, s, e, gl, visited, levels, next_level, b0, b1, nq, counters);
+            td_expand<G, PART>(ptr, adj, s, e, gl, visited, levels, next_level, b0, b1, nq, counters, mf);
         }
     }
     edges = warp_sum_i64(edges);
+    mf = warp_sum_i64(mf);
     if (lane == 0 && edges) atomicAdd(&counters[C_EDGES], (unsigned long long)edges);
+    if (lane == 0 && mf) atomicAdd(&counters[C_MF], (unsigned long long)mf);
 }
 
-// sum of out-degrees of the freshly built next frontier (m_f of the direction heuristic)
-__global__ void bfs_queue_degree_kernel(const int64_t *__restrict__ ptr, TierQueues q, int32_t n0, int32_t n1, int32_t n2,
-                                        unsigned long long *counters)
-{
-    const int n = n0 + n1 + n2;
-    long long sum = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    {
-        const int32_t u = i < n0 ? q.q[0][i] : (i < n0 + n1 ? q.q[1][i - n0] : q.q[2][i - n0 - n1]);
-        sum += ptr[u + 1] - ptr[u];
-    }
-    sum = warp_sum_i64(sum);
-    if ((threadIdx.x & 31) == 0 && sum) atomicAdd(&counters[C_MF], (unsigned long long)sum);
-}
+// bottom-up step. A warp takes 32 consecutive words of the visited bitmap per pass: lane l loads word l (one coalesced
+// 128-byte read instead of 32 broadcast reads) and works out which of its 32 vertices still need a parent; words without
+// such vertices — most of them in the late levels — cost nothing more. Words with work are then processed one at a time
+// by the whole warp, lane l owning vertex l of the word: lane-private probes of the first in-neighbours, four at a time
+// (the four ids and then the four frontier bits are independent loads), then warp-cooperative scans of the long rows
+// with ballot early exit. Bitmap words are written without atomics; in-rows list sources hubs-first.
+#define BFS_BU_WORDS 4
 
-// bottom-up step: one warp per 32-vertex word of the visited bitmap
 __global__ void __launch_bounds__(BFS_THREADS)
-bfs_bu_kernel(const int64_t *__restrict__ in_ptr, const int32_t *__restrict__ in_adj, int32_t V,
+bfs_bu_kernel(const int64_t *__restrict__ in_ptr, const int32_t *__restrict__ in_adj, int32_t V, const uint32_t *__restrict__ no_in_edges,
               uint32_t *__restrict__ visited, const uint32_t *__restrict__ cur_bm, uint32_t *__restrict__ next_bm,
               int32_t *__restrict__ levels, int32_t next_level, unsigned long long *counters)
 {
+    const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t nwords = ((int64_t)V + 31) >> 5;
     long long edges = 0, rows = 0;
     int found_total = 0;
-    for (int64_t w = warp; w < nwords; w += nwarps)
+    for (int64_t wbase = warp * 32; wbase < nwords; wbase += nwarps * 32)
     {
-        const uint32_t vis = visited[w];
-        const int32_t v = (int32_t)(w << 5) + lane;
-        const uint32_t valid = (w == nwords - 1 && (V & 31)) ? ((1u << (V & 31)) - 1u) : 0xffffffffu;
-        const uint32_t unv = ~vis & valid;
-        if (unv == 0)
+        const int64_t wl = wbase + lane;
+        uint32_t vis_l = 0, unv_l = 0;
+        if (wl < nwords)
         {
-            if (lane == 0) next_bm[w] = 0;
-            continue;
+            vis_l = visited[wl];
+            const uint32_t valid = (wl == nwords - 1 && (V & 31)) ? ((1u << (V & 31)) - 1u) : 0xffffffffu;
+            // vertices without in-edges can never be found from below (half of a Kronecker graph): not even their row
+            // pointers are read
+            unv_l = ~vis_l & valid & ~no_in_edges[wl];
+            if (unv_l == 0) next_bm[wl] = 0;
         }
-        const bool mine = (unv >> lane) & 1u;
-        bool found = false;
-        int64_t s = 0, e = 0;
-        if (mine)
+        unsigned work = __ballot_sync(FULL, unv_l != 0);
+        while (work)
         {
-            s = in_ptr[v];
-            e = in_ptr[v + 1];
-            rows++;
-            const int64_t pe = min(e, s + BFS_BU_PROBE);
-            for (int64_t p = s; p < pe; p++)
+            // up to BFS_BU_WORDS words with work are in flight together: the pass is a chain of dependent memory accesses
+            // (row pointers -> first in-neighbours -> their frontier bits), so independent words hide each other's latency
+            int jw[BFS_BU_WORDS];
+            uint32_t unv[BFS_BU_WORDS];
+#pragma unroll
+            for (int t = 0; t < BFS_BU_WORDS; t++)
             {
-                edges++;
-                if (bm_test(cur_bm, in_adj[p]))
+                jw[t] = work ? __ffs(work) - 1 : -1;
+                work &= work - 1;
+                unv[t] = jw[t] >= 0 ? __shfl_sync(FULL, unv_l, jw[t]) : 0u;
+            }
+            int64_t s[BFS_BU_WORDS], e[BFS_BU_WORDS];
+#pragma unroll
+            for (int t = 0; t < BFS_BU_WORDS; t++)
+            {
+                s[t] = 0;
+                e[t] = 0;
+                if ((unv[t] >> lane) & 1u)
                 {
-                    found = true;
-                    break;
+                    const int64_t v = ((wbase + jw[t]) << 5) + lane;
+                    s[t] = in_ptr[v];
+                    e[t] = in_ptr[v + 1];
+                    rows++;
                 }
             }
-        }
-        // rows longer than the probe: finished by the whole warp, 32 neighbours at a time
-        unsigned pending = __ballot_sync(0xffffffffu, mine && !found && (s + BFS_BU_PROBE < e));
-        while (pending)
-        {
-            const int src_lane = __ffs(pending) - 1;
-            pending &= pending - 1;
-            const int64_t ps = __shfl_sync(0xffffffffu, s, src_lane) + BFS_BU_PROBE;
-            const int64_t pe = __shfl_sync(0xffffffffu, e, src_lane);
-            bool hit = false;
-            for (int64_t p0 = ps; p0 < pe; p0 += 32)
+            int32_t x[BFS_BU_WORDS][BFS_BU_PROBE];
+#pragma unroll
+            for (int t = 0; t < BFS_BU_WORDS; t++)
+#pragma unroll
+                for (int k = 0; k < BFS_BU_PROBE; k++) x[t][k] = s[t] + k < e[t] ? in_adj[s[t] + k] : -1;
+            bool found[BFS_BU_WORDS];
+#pragma unroll
+            for (int t = 0; t < BFS_BU_WORDS; t++)
             {
-                const int64_t p = p0 + lane;
-                bool h = false;
-                if (p < pe)
+                found[t] = false;
+#pragma unroll
+                for (int k = 0; k < BFS_BU_PROBE; k++)
+                    if (x[t][k] >= 0)
+                    {
+                        edges++;
+                        found[t] |= bm_test(cur_bm, x[t][k]);
+                    }
+            }
+#pragma unroll
+            for (int t = 0; t < BFS_BU_WORDS; t++)
+            {
+                if (jw[t] < 0) break;
+                const int64_t w = wbase + jw[t];
+                bool fnd = found[t];
+                // further lane-private probes, four at a time, up to BFS_BU_PROBE_MAX in-neighbours
+                const int64_t pe = min(e[t], s[t] + BFS_BU_PROBE_MAX);
+                for (int64_t p = s[t] + BFS_BU_PROBE; p < pe && !fnd; p += BFS_BU_PROBE)
                 {
-                    edges++;
-                    h = bm_test(cur_bm, in_adj[p]);
+                    int32_t y[BFS_BU_PROBE];
+#pragma unroll
+                    for (int k = 0; k < BFS_BU_PROBE; k++) y[k] = p + k < pe ? in_adj[p + k] : -1;
+#pragma unroll
+                    for (int k = 0; k < BFS_BU_PROBE; k++)
+                        if (y[k] >= 0)
+                        {
+                            edges++;
+                            fnd |= bm_test(cur_bm, y[k]);
+                        }
                 }
-                if (__any_sync(0xffffffffu, h))
+                // rows longer than the probe: finished by the whole warp, 32 neighbours at a time
+                unsigned pending = __ballot_sync(FULL, !fnd && (s[t] + BFS_BU_PROBE_MAX < e[t]));
+                while (pending)
                 {
-                    hit = true;
-                    break;
+                    const int src_lane = __ffs(pending) - 1;
+                    pending &= pending - 1;
+                    const int64_t ps = __shfl_sync(FULL, s[t], src_lane) + BFS_BU_PROBE_MAX;
+                    const int64_t pend = __shfl_sync(FULL, e[t], src_lane);
+                    bool hit = false;
+                    for (int64_t p0 = ps; p0 < pend; p0 += 32)
+                    {
+                        const int64_t p = p0 + lane;
+                        bool h = false;
+                        if (p < pend)
+                        {
+                            edges++;
+                            h = bm_test(cur_bm, in_adj[p]);
+                        }
+                        if (__any_sync(FULL, h))
+                        {
+                            hit = true;
+                            break;
+                        }
+                    }
+                    if (lane == src_lane && hit) fnd = true;
+                }
+                const uint32_t fmask = __ballot_sync(FULL, fnd);
+                if (fnd) levels[(w << 5) + lane] = next_level;
+                if (lane == jw[t])
+                {
+                    next_bm[w] = fmask;
+                    if (fmask) visited[w] = vis_l | fmask;
+                    found_total += __popc(fmask);
                 }
             }
-            if (lane == src_lane && hit) found = true;
-        }
-        const uint32_t fmask = __ballot_sync(0xffffffffu, found);
-        if (found) levels[v] = next_level;
-        if (lane == 0)
-        {
-            next_bm[w] = fmask;
-            if (fmask) visited[w] = vis | fmask;
-            found_total += __popc(fmask);
         }
     }
     edges = warp_sum_i64(edges);
     rows = warp_sum_i64(rows);
+    found_total = (int)warp_sum_i64(found_total);
     if (lane == 0)
     {
         if (edges) atomicAdd(&counters[C_EDGES], (unsigned long long)edges);
         if (rows) atomicAdd(&counters[C_ROWS], (unsigned long long)rows);
         if (found_total) atomicAdd(&counters[C_FOUND], (unsigned long long)found_total);
     }
+}
+
+// bit v = vertex v has no in-edges (built once per graph)
+__global__ void bfs_no_in_edges_kernel(const int64_t *__restrict__ in_ptr, int32_t V, uint32_t *__restrict__ out)
+{
+    const int32_t padded = (V + 31) & ~31;
+    for (int32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < padded; v += gridDim.x * blockDim.x)
+    {
+        const bool none = v >= V || in_ptr[v + 1] == in_ptr[v];
+        const uint32_t word = __ballot_sync(0xffffffffu, none);
+        if ((threadIdx.x & 31) == 0) out[v >> 5] = word;
+    }
+}
+
+static int bfs_prepare_no_in_edges(vglb_ctx *ctx, vglb_graph *g)
+{
+    if (g->d_scratch_i32 || !g->d_in_ptr) return VGLB_OK;
+    CUDA_TRY(cudaMalloc(&g->d_scratch_i32, (((size_t)g->V + 31) / 32 + 32) * 4));
+    bfs_no_in_edges_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(g->d_in_ptr, g->V, (uint32_t *)g->d_scratch_i32);
+    KERNEL_TRY();
+    ctx->launches++;
+    return VGLB_OK;
 }
 
 // sparse queues -> dense bitmap (bitmap must be zeroed before)
@@ -378,6 +510,7 @@ static int bfs_partitioned(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t
     const long long alpha = (opts && opts->alpha > 0) ? opts->alpha : 15;
     const long long beta = (opts && opts->beta > 0) ? opts->beta : 18;
     CUDA_TRY(cudaSetDevice(ctx->device));
+    int rc0;
     vglb_comm *comm = g->comm;
     const int32_t P = g->part_world, rank = g->part_rank, vp = g->vp, rows = g->V;
     const int32_t wslice = vp / 32;
@@ -386,6 +519,8 @@ static int bfs_partitioned(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t
         if (!g->d_part_bm[i]) CUDA_TRY(cudaMalloc(&g->d_part_bm[i], (size_t)(words + 32) * 4));
     if (!g->d_part_stage) CUDA_TRY(cudaMalloc(&g->d_part_stage, (size_t)(words + 32) * 4));
     if (!g->d_queue[0]) CUDA_TRY(cudaMalloc(&g->d_queue[0], ((size_t)vp + 3) * 4));
+    rc0 = bfs_prepare_no_in_edges(ctx, g);
+    if (rc0 != VGLB_OK) return rc0;
     const int64_t launches0 = ctx->launches;
     const int32_t b0 = g->tier_border[0], b1 = g->tier_border[1];
     unsigned long long *d_cnt = (unsigned long long *)ctx->d_counters;
@@ -420,6 +555,7 @@ static int bfs_partitioned(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t
     const long long Vg = g->V_orig;
     const long long factor = (g->E_global / (Vg > 0 ? Vg : 1)) / 2 > 0 ? (g->E_global / Vg) / 2 : 1;
     const int max_blocks = ctx->sm_count * 16;
+    const int big_chunks = (int)ceil_div64(g->max_degree > 0 ? g->max_degree : 1, BFS_BIG_CHUNK);
     int rc;
 
     while (n_cur > 0)
@@ -429,10 +565,10 @@ static int bfs_partitioned(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t
             CUDA_TRY(cudaMemsetAsync(next_bm, 0, (size_t)words * 4, st)); // candidates
             const int blocks_mid = (int)min((int64_t)max_blocks, ceil_div64(n[1], BFS_THREADS / 32));
             const int blocks_small = (int)min((int64_t)max_blocks, ceil_div64(n[2], BFS_THREADS / BFS_SMALL_LANES));
-            const int64_t grid = (int64_t)n[0] + blocks_mid + blocks_small;
+            const int64_t grid = (int64_t)n[0] * big_chunks + blocks_mid + blocks_small;
             if (grid > 0)
             {
-                bfs_td_kernel<true><<<(unsigned)grid, BFS_THREADS, 0, st>>>(g->d_out_ptr, g->d_out_adj, cq, n[0], n[1], n[2], blocks_mid,
+                bfs_td_kernel<true><<<(unsigned)grid, BFS_THREADS, 0, st>>>(g->d_out_ptr, g->d_out_adj, cq, n[0], big_chunks, n[1], n[2], blocks_mid,
                                                                           blocks_small, visited, (int32_t *)next_bm, level + 1, b0, b1,
                                                                           cq, d_cnt);
                 KERNEL_TRY();
@@ -449,7 +585,7 @@ static int bfs_partitioned(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t
         else
         {
             CUDA_TRY(cudaMemsetAsync(next_bm + my, 0, (size_t)wslice * 4, st));
-            bfs_bu_kernel<<<ctx->sm_count * 8, BFS_THREADS, 0, st>>>(g->d_in_ptr, g->d_in_adj, rows, visited + my, cur_bm,
+            bfs_bu_kernel<<<ctx->sm_count * 8, BFS_THREADS, 0, st>>>(g->d_in_ptr, g->d_in_adj, rows, (const uint32_t *)g->d_scratch_i32, visited + my, cur_bm,
                                                                     next_bm + my, d_levels, level + 1, d_cnt);
             KERNEL_TRY();
             ctx->launches++;
@@ -542,7 +678,7 @@ static int bfs_prepare(vglb_ctx *ctx, vglb_graph *g)
     CUDA_TRY(cudaMalloc(&g->d_queue[0], ((size_t)g->V + 3) * 4));
     CUDA_TRY(cudaMalloc(&g->d_queue[1], ((size_t)g->V + 3) * 4));
     g->bfs_ready = 1;
-    return VGLB_OK;
+    return bfs_prepare_no_in_edges(ctx, g);
 }
 
 extern "C" int vglb_bfs(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t *d_levels, const vglb_bfs_opts *opts,
@@ -599,6 +735,14 @@ extern "C" int vglb_bfs(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t *d
     int32_t bu_levels = 0;
     const long long factor = (g->E / (V > 0 ? V : 1)) / 2 > 0 ? (g->E / V) / 2 : 1; // change_state.hpp:104
     const int max_blocks = ctx->sm_count * 16;
+    const int big_chunks = (int)ceil_div64(g->max_degree > 0 ? g->max_degree : 1, BFS_BIG_CHUNK);
+    const bool trace = getenv("VGLB_BFS_TRACE") != NULL; // developer aid: one line per level on stderr
+    double trace_t = 0.0;
+    if (trace)
+    {
+        cudaStreamSynchronize(st);
+        trace_t = trace_now();
+    }
 
     while (n_cur > 0)
     {
@@ -606,8 +750,8 @@ extern "C" int vglb_bfs(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t *d
         {
             const int blocks_mid = (int)min((int64_t)max_blocks, ceil_div64(n[1], BFS_THREADS / 32));
             const int blocks_small = (int)min((int64_t)max_blocks, ceil_div64(n[2], BFS_THREADS / BFS_SMALL_LANES));
-            const int64_t grid = (int64_t)n[0] + blocks_mid + blocks_small;
-            bfs_td_kernel<false><<<(unsigned)grid, BFS_THREADS, 0, st>>>(g->d_out_ptr, g->d_out_adj, cq, n[0], n[1], n[2], blocks_mid,
+            const int64_t grid = (int64_t)n[0] * big_chunks + blocks_mid + blocks_small;
+            bfs_td_kernel<false><<<(unsigned)grid, BFS_THREADS, 0, st>>>(g->d_out_ptr, g->d_out_adj, cq, n[0], big_chunks, n[1], n[2], blocks_mid,
                                                                  blocks_small, g->d_visited, d_levels, level + 1, b0, b1, nq,
                                                                  d_cnt);
             KERNEL_TRY();
@@ -616,7 +760,7 @@ extern "C" int vglb_bfs(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t *d
         }
         else
         {
-            bfs_bu_kernel<<<ctx->sm_count * 8, BFS_THREADS, 0, st>>>(g->d_in_ptr, g->d_in_adj, V, g->d_visited, cur_bm,
+            bfs_bu_kernel<<<ctx->sm_count * 8, BFS_THREADS, 0, st>>>(g->d_in_ptr, g->d_in_adj, V, (const uint32_t *)g->d_scratch_i32, g->d_visited, cur_bm,
                                                                     next_bm, d_levels, level + 1, d_cnt);
             KERNEL_TRY();
             ctx->launches++;
@@ -633,6 +777,13 @@ extern "C" int vglb_bfs(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t *d
         if (bottom_up) tot_rows += (long long)h_cnt[C_ROWS];
         else tot_frontier_bytes += 8 * n_next; // queue written now, read next level
         visited_total += n_next;
+        if (trace)
+        {
+            const double now = trace_now();
+            fprintf(stderr, "bfs level %d (%s): frontier %lld, inspected %lld edges, found %lld, %.1f us since the previous line\n", level,
+                    bottom_up ? "bottom-up" : "top-down", n_cur, in_lvl, n_next, (now - trace_t) * 1e6);
+            trace_t = now;
+        }
         if (n_next == 0) break;
 
         // direction switch — gpu_change_state (change_state.hpp:100-141) evaluated on the device counters; the
@@ -643,14 +794,7 @@ extern "C" int vglb_bfs(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t *d
             const long long unvisited = (long long)V - visited_total;
             if (!bottom_up && n_cur < n_next)
             {
-                CUDA_TRY(cudaMemsetAsync(d_cnt + C_MF, 0, 8, st));
-                bfs_queue_degree_kernel<<<(unsigned)min((int64_t)max_blocks, ceil_div64(n_next, 256)), 256, 0, st>>>(
-                    g->d_out_ptr, nq, nn[0], nn[1], nn[2], d_cnt);
-                KERNEL_TRY();
-                ctx->launches++;
-                CUDA_TRY(cudaMemcpyAsync(h_cnt + C_MF, d_cnt + C_MF, 8, cudaMemcpyDeviceToHost, st));
-                CUDA_TRY(cudaStreamSynchronize(st));
-                const long long m_f = (long long)h_cnt[C_MF];
+                const long long m_f = (long long)h_cnt[C_MF]; // accumulated by the advance itself
                 if (m_f >= (unvisited * factor + V) / alpha) next_bu = true;
             }
             else if (bottom_up && n_cur >= n_next)
