@@ -61,9 +61,14 @@ __device__ __forceinline__ void pr_epilogue(const PrParams &P, const L2Pol &pol,
     const float inv_r = ld_stream_f32(P.inv + row, pol.stream);
     // k + d * (rank + dangling) — pr.hpp:118-121, no FMA contraction (the x86-64 reference build has none)
     const float rank = __fadd_rn(P.k, __fmul_rn(P.d, __fadd_rn(sum, dang)));
-    const float c = __fmul_rn(rank, inv_r);
-    st_stream_f32(P.contrib_out + row, c);
-    for (int p = 0; p < P.npeers; p++) st_stream_f32(P.peer_out[p] + row, c);
+    // a vertex nobody points to (inv == 0: 55-60 % of an RMAT graph) contributes exactly 0 in every sweep: both vectors
+    // are zero-filled once and its slot is never written again — neither locally nor into the peers' copies over NVLink
+    if (inv_r != 0.0f)
+    {
+        const float c = __fmul_rn(rank, inv_r);
+        st_stream_f32(P.contrib_out + row, c);
+        for (int p = 0; p < P.npeers; p++) st_stream_f32(P.peer_out[p] + row, c);
+    }
     if (P.rank_out) st_stream_f32(P.rank_out + row, rank);
     if (inv_r == 0.0f) dang_local += (double)__fdiv_rn(rank, P.v_as_float); // pr.hpp:94-101
 }
@@ -656,8 +661,9 @@ extern "C" int vglb_pagerank(vglb_ctx *ctx, vglb_graph *g, int iters, float damp
     // them into the peers' vectors (then the dangling-mass allreduce is also the barrier between sweeps: a rank starts
     // sweep i+1 only after every peer finished sweep i, i.e. finished both reading buffer i and writing buffer i+1)
     const bool p2p = comm && g->pr_exchange == VGLB_EXCHANGE_P2P;
+    const bool no_exchange = getenv("VGLB_PR_NO_EXCHANGE") != NULL; // developer knob: time one rank's sweeps alone (results are wrong)
     auto exchange = [&](float *vec, double *dangling, bool stored_by_peers) -> int {
-        if (!comm) return VGLB_OK;
+        if (!comm || no_exchange) return VGLB_OK;
         if (!stored_by_peers)
         {
             int rc = vglb_comm_allgather_async(comm, vec, (size_t)g->vp * 4);
