@@ -97,6 +97,8 @@ struct vglb_graph
     // PageRank peer-store exchange: the peers' copies of the two contribution vectors (CUDA IPC mappings)
     int pr_exchange;            // VGLB_EXCHANGE_NCCL | VGLB_EXCHANGE_P2P
     float *d_pr_peer[2][8];     // [buffer][peer rank]; NULL for this rank
+    uint32_t *d_vec_peer[8];    // the peers' d_part_vec (SSSP distance replicas), CUDA IPC mappings; NULL for this rank
+    int vec_peers_mapped;       // 0 = not tried, 1 = mapped, -1 = mapping failed (dense allreduce exchange is used)
     // BFS / SSSP / CC scratch
     uint32_t *d_visited, *d_front_bm[2];
     int32_t *d_queue[2];
@@ -145,6 +147,7 @@ enum { VGLB_OP_SUM = 0, VGLB_OP_MIN = 1, VGLB_OP_MAX = 2 };
 int vglb_comm_allgather_async(vglb_comm *comm, void *d_buf, size_t bytes_per_rank);
 int vglb_comm_allreduce_async(vglb_comm *comm, void *d_buf, size_t count, int dtype, int op);
 int vglb_comm_alltoall_async(vglb_comm *comm, const void *d_send, void *d_recv, size_t bytes_per_rank);
+int vglb_comm_ipc_map(vglb_comm *comm, void *d_local, void **peers /* [world] */);
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -193,6 +193,8 @@ void vglb_graph_free_fields(vglb_graph *g)
     for (int b = 0; b < 2; b++)
         for (int p = 0; p < 8; p++)
             if (g->d_pr_peer[b][p]) cudaIpcCloseMemHandle(g->d_pr_peer[b][p]);
+    for (int p = 0; p < 8; p++)
+        if (g->d_vec_peer[p] && p != g->part_rank) cudaIpcCloseMemHandle(g->d_vec_peer[p]);
     cudaFree(g->d_out_ptr); cudaFree(g->d_out_adj); cudaFree(g->d_in_ptr); cudaFree(g->d_in_adj);
     cudaFree(g->d_fwd); cudaFree(g->d_bwd); cudaFree(g->d_edge_order);
     cudaFree(g->d_pr_inv); cudaFree(g->d_pr_contrib[0]); cudaFree(g->d_pr_contrib[1]); cudaFree(g->d_pr_dangling); cudaFree(g->d_pr_tasks); cudaFree(g->d_pr_piece_partial); cudaFree(g->d_pr_piece_count); cudaFree(g->d_pr_ve_adj); cudaFree(g->d_pr_ve_ptr);

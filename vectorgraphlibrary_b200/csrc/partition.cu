@@ -209,6 +209,41 @@ int vglb_comm_alltoall_async(vglb_comm *comm, const void *d_send, void *d_recv, 
     return VGLB_OK;
 }
 
+// Map a cudaMalloc'ed buffer of every rank into this process (CUDA IPC; NVLink peer access): peers[q] = rank q's buffer,
+// peers[rank] = d_local. The handles travel through the communicator (an allgather of 64 bytes per rank).
+int vglb_comm_ipc_map(vglb_comm *comm, void *d_local, void **peers)
+{
+    DETACHED_CHECK(comm);
+    vglb_ctx *ctx = comm->ctx;
+    const int P = comm->world, rank = comm->rank;
+    const size_t hb = sizeof(cudaIpcMemHandle_t);
+    cudaIpcMemHandle_t mine;
+    CUDA_TRY(cudaIpcGetMemHandle(&mine, d_local));
+    char *d_all = NULL;
+    CUDA_TRY(cudaMalloc(&d_all, (size_t)P * hb));
+    CUDA_TRY(cudaMemcpyAsync(d_all + (size_t)rank * hb, &mine, hb, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = vglb_comm_allgather_async(comm, d_all, hb);
+    if (rc != VGLB_OK) { cudaFree(d_all); return rc; }
+    cudaIpcMemHandle_t all[64];
+    CUDA_TRY(cudaMemcpyAsync(all, d_all, (size_t)P * hb, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_all);
+    for (int q = 0; q < P; q++)
+    {
+        if (q == rank) { peers[q] = d_local; continue; }
+        void *ptr = NULL;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, all[q], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess)
+        {
+            cudaGetLastError();
+            vglb_set_error("vglb_comm_ipc_map: cudaIpcOpenMemHandle of rank %d failed: %s", q, cudaGetErrorString(e));
+            return VGLB_ECUDA;
+        }
+        peers[q] = ptr;
+    }
+    return VGLB_OK;
+}
+
 extern "C" int vglb_comm_allgather(vglb_comm *comm, void *d_buf, size_t bytes_per_rank)
 {
     VGLB_REQUIRE(comm != NULL && d_buf != NULL, "vglb_comm_allgather: NULL argument");

@@ -92,7 +92,7 @@ sssp_relax_rows_kernel(const int64_t *__restrict__ ptr, const int32_t *__restric
     if (lane == 0 && edges) atomicAdd(&counters[C_EDGES], (unsigned long long)edges);
 }
 
-// ---- 1D-partitioned SSSP ---------------------------------------------------------------------------------------------
+// ---- 1D-partitioned SSSP, dense exchange (fallback when the peers' replicas cannot be mapped) ---------------------------------------------------------------------------------------------
 // Each rank relaxes the out-edges of the frontier vertices it owns into its replica of the distance vector (atomicMin),
 // the replicas are combined with one allreduce(min) on the uint32 view per round — the reference MPI_Allreduce(MIN)es
 // the same array after its advance (mpi_exchange.hpp:155-271, gpu_shortest_paths.hpp:133-196) — and every owner queues
@@ -136,7 +136,7 @@ __global__ void sssp_copy_counters_kernel(unsigned long long *c)
     if (threadIdx.x < C_COUNT) c[C_COUNT + threadIdx.x] = c[threadIdx.x];
 }
 
-static int sssp_partitioned(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, int32_t source, float *d_dist,
+static int sssp_partitioned_dense(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, int32_t source, float *d_dist,
                             vglb_stats *stats)
 {
     VGLB_REQUIRE(source >= 0 && source < g->cols, "vglb_sssp: source column out of range");
@@ -247,16 +247,22 @@ static int sssp_partitioned(vglb_ctx *ctx, vglb_graph *g, const float *d_weights
 // relax one edge: atomicMin on the uint32 view after a plain read that filters the losers; the winner marks the vertex
 // as due in the near (new distance below the threshold) or the far bitmap
 __device__ __forceinline__ void sssp_relax_one(uint32_t *__restrict__ dist, uint32_t *__restrict__ near_bm,
-                                               uint32_t *__restrict__ far_bm, uint32_t threshold_bits, int32_t v, uint32_t c)
+                                               uint32_t *__restrict__ far_bm, uint32_t *__restrict__ changed_bm, int32_t col0,
+                                               int32_t vp, uint32_t threshold_bits, int32_t v, uint32_t c)
 {
     if (c < dist[v])
     {
         const uint32_t old = atomicMin(&dist[v], c);
         if (c < old)
         {
-            uint32_t *bm = c < threshold_bits ? near_bm : far_bm;
-            const uint32_t bit = 1u << (v & 31);
-            if (!(bm[v >> 5] & bit)) atomicOr(&bm[v >> 5], bit);
+            // a vertex of this rank's slice (every vertex on one GPU) becomes due here; a vertex owned by a peer is
+            // flagged in the changed bitmap, whose slices go to the owners after the round
+            const uint32_t r = (uint32_t)(v - col0);
+            const bool local = r < (uint32_t)vp;
+            uint32_t *bm = local ? (c < threshold_bits ? near_bm : far_bm) : changed_bm;
+            const uint32_t i = local ? r : (uint32_t)v;
+            const uint32_t bit = 1u << (i & 31);
+            if (!(bm[i >> 5] & bit)) atomicOr(&bm[i >> 5], bit);
         }
     }
 }
@@ -265,7 +271,8 @@ __global__ void __launch_bounds__(SSSP_THREADS)
 sssp_relax_flat_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, const float *__restrict__ wgt,
                        TierQueues cq, int32_t n_big, int32_t n_mid, int32_t n_small, int32_t per_warp,
                        uint32_t *__restrict__ dist, uint32_t *__restrict__ near_bm, uint32_t *__restrict__ far_bm,
-                       uint32_t threshold_bits, unsigned long long *counters)
+                       uint32_t *__restrict__ changed_bm, int32_t col0, int32_t vp, uint32_t threshold_bits,
+                       unsigned long long *counters)
 {
     const unsigned FULL = 0xffffffffu;
     const uint64_t pol = l2_policy_evict_first();
@@ -276,13 +283,13 @@ sssp_relax_flat_kernel(const int64_t *__restrict__ ptr, const int32_t *__restric
         // a row with >= 4096 edges: the whole CTA strides it
         const int32_t u = cq.q[0][blockIdx.x];
         const int64_t s = ptr[u], e = ptr[u + 1];
-        const float du = __uint_as_float(dist[u]);
+        const float du = __uint_as_float(dist[col0 + u]);
         if (threadIdx.x == 0) edges = e - s;
         for (int64_t p = s + threadIdx.x; p < e; p += SSSP_THREADS)
         {
             const int32_t v = ld_stream_s32(adj + p, pol);
             const uint32_t c = __float_as_uint(__fadd_rn(du, ld_stream_f32(wgt + p, pol)));
-            sssp_relax_one(dist, near_bm, far_bm, threshold_bits, v, c);
+            sssp_relax_one(dist, near_bm, far_bm, changed_bm, col0, vp, threshold_bits, v, c);
         }
     }
     else
@@ -304,7 +311,7 @@ sssp_relax_flat_kernel(const int64_t *__restrict__ ptr, const int32_t *__restric
                 const int32_t u = q[i];
                 s = ptr[u];
                 deg = (int)(ptr[u + 1] - s);
-                du = __uint_as_float(dist[u]);
+                du = __uint_as_float(dist[col0 + u]);
             }
             int incl = deg;
 #pragma unroll
@@ -346,21 +353,14 @@ sssp_relax_flat_kernel(const int64_t *__restrict__ ptr, const int32_t *__restric
 #pragma unroll
                 for (int k = 0; k < SSSP_FLAT_UNROLL; k++)
                 {
-                    if (v[k] >= 0) sssp_relax_one(dist, near_bm, far_bm, threshold_bits, v[k], __float_as_uint(cand[k]));
+                    if (v[k] >= 0)
+                        sssp_relax_one(dist, near_bm, far_bm, changed_bm, col0, vp, threshold_bits, v[k], __float_as_uint(cand[k]));
                 }
             }
         }
     }
     edges = warp_sum_i64(edges);
     if (lane == 0 && edges) atomicAdd(&counters[C_EDGES], (unsigned long long)edges);
-}
-
-__global__ void sssp_init_kernel(uint32_t *__restrict__ dist, int32_t V, int32_t source, int32_t *queue_slot)
-{
-    const uint32_t inf_bits = __float_as_uint(FLT_MAX - 100.0f); // shortest_paths.hpp:22
-    for (int32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x)
-        dist[v] = v == source ? 0u : inf_bits;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *queue_slot = source;
 }
 
 // frontier selection of one round (generate_new_frontier, shortest_paths.hpp:58-66) from the due bitmaps: one thread
@@ -466,8 +466,6 @@ sssp_select_kernel(uint32_t *__restrict__ near_bm, uint32_t *__restrict__ far_bm
     }
 }
 
-__global__ void sssp_seed_kernel(uint32_t *near_bm, int32_t source) { near_bm[source >> 5] = 1u << (source & 31); }
-
 // largest weight among a sample of the edge array (threshold step of the near/far split)
 __global__ void sssp_weight_sample_kernel(const float *__restrict__ w, int64_t E, int64_t stride, unsigned int *out)
 {
@@ -479,73 +477,158 @@ __global__ void sssp_weight_sample_kernel(const float *__restrict__ w, int64_t E
     if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
 }
 
-// Schedule. The reference relaxes the out-edges of EVERY vertex whose distance changed in the previous round
-// (shortest_paths.hpp:40-66); on the BASELINE graph that re-relaxes each edge ~5.6 times. The fixed point
-// does not depend on the schedule, so the frontier is split near/far: only due vertices with dist < threshold are
-// relaxed; when none is left the threshold moves to (smallest pending distance + delta). delta = sampled max weight *
-// VGLB_SSSP_DELTA_SCALE / average degree (default scale 4; 0 or a huge value = the reference's plain schedule).
-// Distances stay bit-exact (same min-plus fixed point); edges_inspected reports the edges actually relaxed.
-extern "C" int vglb_sssp(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, int32_t source, float *d_dist,
-                         vglb_stats *stats)
+// owner side of the sparse exchange of a partitioned round: stage holds, for every peer, the slice of its changed bitmap
+// that covers THIS rank's vertices. For every flagged vertex the owner reads the peer's value straight out of the peer's
+// distance replica (CUDA IPC peer memory over NVLink: 4 bytes per update instead of an allreduce of the whole vector),
+// keeps the minimum and marks the vertex due. One thread per 32-vertex word: no atomics.
+__global__ void __launch_bounds__(256)
+sssp_pull_kernel(const uint32_t *__restrict__ stage, int32_t P, int32_t rank, int32_t wslice, int32_t col0, uint32_t *__restrict__ dist,
+                 const uint32_t *const *__restrict__ peer_dist, uint32_t *__restrict__ near_bm, uint32_t *__restrict__ far_bm,
+                 uint32_t threshold_bits, unsigned long long *counters)
 {
-    VGLB_REQUIRE(ctx != NULL && g != NULL && d_dist != NULL, "vglb_sssp: NULL argument");
-    VGLB_REQUIRE(d_weights != NULL || g->E == 0, "vglb_sssp: NULL weights");
-    if (g->comm) return sssp_partitioned(ctx, g, d_weights, source, d_dist, stats);
-    VGLB_REQUIRE(source >= 0 && source < g->V, "vglb_sssp: source out of range");
+    const int32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    long long pulled = 0;
+    if (w < wslice)
+    {
+        uint32_t near_add = 0, far_add = 0;
+        for (int p = 0; p < P; p++)
+        {
+            if (p == rank) continue;
+            uint32_t bits = stage[(int64_t)p * wslice + w];
+            const uint32_t *remote = peer_dist[p];
+            while (bits)
+            {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const int32_t col = col0 + (w << 5) + b;
+                const uint32_t val = remote[col];
+                pulled++;
+                if (val < dist[col])
+                {
+                    dist[col] = val;
+                    if (val < threshold_bits) near_add |= 1u << b;
+                    else far_add |= 1u << b;
+                }
+            }
+        }
+        if (near_add) near_bm[w] |= near_add;
+        if (far_add) far_bm[w] |= far_add & ~near_add;
+    }
+    pulled = warp_sum_i64(pulled);
+    if ((threadIdx.x & 31) == 0 && pulled) atomicAdd(&counters[C_ROWS], (unsigned long long)pulled);
+}
+
+__global__ void sssp_part_seed_kernel(uint32_t *__restrict__ dist, int64_t cols, int32_t source_col, uint32_t *near_bm, int32_t src_row)
+{
+    const uint32_t inf_bits = __float_as_uint(FLT_MAX - 100.0f);
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < cols; v += (int64_t)gridDim.x * blockDim.x)
+        dist[v] = v == source_col ? 0u : inf_bits;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && src_row >= 0) near_bm[src_row >> 5] = 1u << (src_row & 31);
+}
+
+// counters [0, C_COUNT) -> [C_COUNT, 2 C_COUNT) (summed over ranks) and the pending minimum -> slot 2 C_COUNT (max over ranks)
+__global__ void sssp_stage_counters_kernel(unsigned long long *c)
+{
+    if (threadIdx.x < C_COUNT) c[C_COUNT + threadIdx.x] = c[threadIdx.x];
+    if (threadIdx.x == 0) c[2 * C_COUNT] = c[C_MF];
+}
+
+// Schedule. The reference relaxes the out-edges of EVERY vertex whose distance changed in the previous round
+// (shortest_paths.hpp:40-66); on the BASELINE graph that re-relaxes each edge ~5.8 times. The fixed point does not
+// depend on the schedule, so the frontier is split near/far: only due vertices with dist < threshold are relaxed; when
+// none is left the threshold moves up by delta (or jumps to the smallest pending distance + delta).
+// delta = sampled max weight * VGLB_SSSP_DELTA_SCALE / average degree (default scale 4; 0 = the reference's plain schedule).
+// Distances stay bit-exact (same min-plus fixed point); edges_inspected reports the edges actually relaxed.
+//
+// One driver serves one GPU and a 1D-partitioned graph (g->comm != NULL). Partitioned: every rank relaxes the due
+// vertices it owns into its own replica of the distance vector; vertices of its own slice become due on the spot,
+// vertices owned by peers are flagged in a changed bitmap. After the round the bitmap slices go to the owners
+// (all-to-all, V/8/P bytes per pair), each owner pulls the flagged values out of the peers' replicas (sssp_pull_kernel)
+// and the round's counters are allreduced so that every rank takes the same scheduling decision. The reference's MPI
+// build allreduces the whole array after every advance instead (mpi_exchange.hpp:155-271). When the peers' replicas
+// cannot be mapped (no CUDA IPC), sssp_partitioned_dense (allreduce(min) of the vector, plain schedule) is used.
+static int sssp_run(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, int32_t source, float *d_dist, vglb_stats *stats)
+{
     CUDA_TRY(cudaSetDevice(ctx->device));
+    vglb_comm *comm = g->comm;
+    const bool part = comm != NULL;
+    const int32_t rows = g->V, vp = part ? g->vp : g->V, col0 = g->col_of_row0, P = g->part_world, rank = g->part_rank;
+    const int32_t b0 = g->tier_border[0], b1 = g->tier_border[1];
+    const size_t words = ((size_t)vp + 31) / 32;          // bitmaps over this rank's rows
+    const int32_t wslice = (int32_t)words;
+    const size_t words_full = (size_t)(g->cols + 31) / 32;  // changed bitmap over all columns
     if (!g->d_queue[0])
     {
-        CUDA_TRY(cudaMalloc(&g->d_queue[0], ((size_t)g->V + 3) * 4));
-        CUDA_TRY(cudaMalloc(&g->d_queue[1], ((size_t)g->V + 3) * 4));
+        CUDA_TRY(cudaMalloc(&g->d_queue[0], ((size_t)vp + 3) * 4));
+        CUDA_TRY(cudaMalloc(&g->d_queue[1], ((size_t)vp + 3) * 4));
     }
-    const size_t words = ((size_t)g->V + 31) / 32;
     if (!g->d_visited) CUDA_TRY(cudaMalloc(&g->d_visited, (words + 32) * 4));
     if (!g->d_front_bm[0]) CUDA_TRY(cudaMalloc(&g->d_front_bm[0], (words + 32) * 4));
+    uint32_t *dist = (uint32_t *)d_dist, *changed_bm = NULL;
+    const uint32_t **d_peer_table = NULL;
+    if (part)
+    {
+        if (!g->d_part_bm[0]) CUDA_TRY(cudaMalloc(&g->d_part_bm[0], (words_full + 32) * 4));
+        if (!g->d_part_stage) CUDA_TRY(cudaMalloc(&g->d_part_stage, (words_full + 32) * 4));
+        dist = g->d_part_vec;
+        changed_bm = g->d_part_bm[0];
+        d_peer_table = (const uint32_t **)(ctx->d_counters + 24); // 8 device pointers
+        CUDA_TRY(cudaMemcpyAsync(d_peer_table, g->d_vec_peer, sizeof(g->d_vec_peer), cudaMemcpyHostToDevice, ctx->stream));
+    }
     const int64_t launches0 = ctx->launches;
-    const int32_t V = g->V, b0 = g->tier_border[0], b1 = g->tier_border[1];
     unsigned long long *d_cnt = (unsigned long long *)ctx->d_counters;
     unsigned long long *h_cnt = (unsigned long long *)ctx->h_counters;
     cudaStream_t st = ctx->stream;
-    uint32_t *dist = (uint32_t *)d_dist, *near_bm = g->d_visited, *far_bm = g->d_front_bm[0];
+    uint32_t *near_bm = g->d_visited, *far_bm = g->d_front_bm[0];
     TierQueues cq;
     cq.q[0] = g->d_queue[0];
     cq.q[1] = g->d_queue[0] + b0;
     cq.q[2] = g->d_queue[0] + b1;
+    int rc;
 
     CUDA_TRY(cudaEventRecord(ctx->ev_start, st));
     // threshold step
     double scale = 4.0;
     if (const char *e = getenv("VGLB_SSSP_DELTA_SCALE")) scale = atof(e);
     float delta = 0.f; // 0 = plain schedule
-    if (scale > 0.0 && g->E > 0)
+    if (scale > 0.0 && g->E_global > 0)
     {
         unsigned int *d_max = (unsigned int *)(d_cnt + 60);
         CUDA_TRY(cudaMemsetAsync(d_max, 0, 4, st));
-        const int64_t stride = g->E > (1 << 22) ? g->E >> 22 : 1;
-        sssp_weight_sample_kernel<<<64, 256, 0, st>>>(d_weights, g->E, stride, d_max);
-        KERNEL_TRY();
-        ctx->launches++;
+        if (g->E > 0)
+        {
+            const int64_t stride = g->E > (1 << 22) ? g->E >> 22 : 1;
+            sssp_weight_sample_kernel<<<64, 256, 0, st>>>(d_weights, g->E, stride, d_max);
+            KERNEL_TRY();
+            ctx->launches++;
+        }
+        if (part)
+        {
+            rc = vglb_comm_allreduce_async(comm, d_max, 1, VGLB_DT_U32, VGLB_OP_MAX); // same delta on every rank
+            if (rc != VGLB_OK) return rc;
+        }
         unsigned int bits = 0;
         CUDA_TRY(cudaMemcpyAsync(&bits, d_max, 4, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         float wmax;
         memcpy(&wmax, &bits, 4);
-        const double avg_deg = (double)g->E / (double)V;
+        const double avg_deg = (double)g->E_global / (double)g->V_orig;
         delta = (float)(scale * (double)wmax / (avg_deg > 1.0 ? avg_deg : 1.0));
     }
     const bool trace = getenv("VGLB_SSSP_TRACE") != NULL; // developer aid: one line per selection on stderr
     const float inf = FLT_MAX - 100.0f;
     const bool split = delta > 0.f && delta < inf;
     float threshold = split ? delta : inf;
-    sssp_init_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(dist, V, source, cq.q[0]);
-    KERNEL_TRY();
     CUDA_TRY(cudaMemsetAsync(near_bm, 0, words * 4, st));
     CUDA_TRY(cudaMemsetAsync(far_bm, 0, words * 4, st));
-    sssp_seed_kernel<<<1, 1, 0, st>>>(near_bm, source);
+    if (part) CUDA_TRY(cudaMemsetAsync(changed_bm, 0, words_full * 4, st));
+    const int32_t src_row = source - col0; // the owner seeds its near bitmap
+    sssp_part_seed_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(dist, part ? g->cols : (int64_t)rows, source, near_bm,
+                                                            (src_row >= 0 && src_row < rows) ? src_row : -1);
     KERNEL_TRY();
-    CUDA_TRY(cudaMemsetAsync(d_cnt, 0, C_COUNT * 8, st));
-    ctx->launches += 2;
-    int64_t tot_edges = 0, tot_rows = 0, tot_next = 0, rounds = 0, selects = 0, far_selects = 0;
+    CUDA_TRY(cudaMemsetAsync(d_cnt, 0, (2 * C_COUNT + 1) * 8, st));
+    ctx->launches++;
+    int64_t tot_edges = 0, tot_rows = 0, tot_next = 0, rounds = 0, selects = 0, far_selects = 0, tot_pulled = 0;
     const unsigned select_grid = (unsigned)ceil_div64((int64_t)words, 256);
     bool from_far = false;
     for (;;)
@@ -553,20 +636,33 @@ extern "C" int vglb_sssp(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, i
         uint32_t tbits;
         if (threshold >= inf) tbits = 0xffffffffu; // everything that is due
         else memcpy(&tbits, &threshold, 4);
-        if (from_far) sssp_select_kernel<true><<<select_grid, 256, 0, st>>>(near_bm, far_bm, dist, V, tbits, b0, b1, cq, d_cnt);
-        else sssp_select_kernel<false><<<select_grid, 256, 0, st>>>(near_bm, far_bm, dist, V, tbits, b0, b1, cq, d_cnt);
+        if (from_far) sssp_select_kernel<true><<<select_grid, 256, 0, st>>>(near_bm, far_bm, dist + col0, rows, tbits, b0, b1, cq, d_cnt);
+        else sssp_select_kernel<false><<<select_grid, 256, 0, st>>>(near_bm, far_bm, dist + col0, rows, tbits, b0, b1, cq, d_cnt);
         KERNEL_TRY();
         ctx->launches++;
         selects++;
         far_selects += from_far;
-        CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, C_COUNT * 8, cudaMemcpyDeviceToHost, st));
+        if (part)
+        {
+            sssp_stage_counters_kernel<<<1, 32, 0, st>>>(d_cnt);
+            KERNEL_TRY();
+            ctx->launches++;
+            rc = vglb_comm_allreduce_async(comm, d_cnt + C_COUNT, C_COUNT, VGLB_DT_I64, VGLB_OP_SUM);
+            if (rc != VGLB_OK) return rc;
+            rc = vglb_comm_allreduce_async(comm, d_cnt + 2 * C_COUNT, 1, VGLB_DT_I64, VGLB_OP_MAX);
+            if (rc != VGLB_OK) return rc;
+        }
+        CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, (2 * C_COUNT + 1) * 8, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        CUDA_TRY(cudaMemsetAsync(d_cnt, 0, C_COUNT * 8, st));
+        CUDA_TRY(cudaMemsetAsync(d_cnt, 0, (2 * C_COUNT + 1) * 8, st));
         const int32_t n[3] = {(int32_t)h_cnt[C_NEXT_BIG], (int32_t)h_cnt[C_NEXT_MID], (int32_t)h_cnt[C_NEXT_SMALL]};
-        const long long n_cur = (long long)n[0] + n[1] + n[2], pending = (long long)h_cnt[C_FOUND];
-        tot_edges += (int64_t)h_cnt[C_EDGES]; // relaxed by the previous round
-        if (trace) fprintf(stderr, "sssp select %lld (%s): threshold %.3f queued %lld pending %lld, previous round relaxed %lld edges\n",
-                           (long long)selects, from_far ? "far" : "near", threshold, n_cur, pending, (long long)h_cnt[C_EDGES]);
+        const unsigned long long *gl = part ? h_cnt + C_COUNT : h_cnt; // whole-job sums drive the schedule
+        const long long n_local = (long long)n[0] + n[1] + n[2];
+        const long long n_cur = (long long)(gl[C_NEXT_BIG] + gl[C_NEXT_MID] + gl[C_NEXT_SMALL]), pending = (long long)gl[C_FOUND];
+        tot_edges += (int64_t)h_cnt[C_EDGES]; // relaxed by the previous round (this rank)
+        tot_pulled += (int64_t)h_cnt[C_ROWS];
+        if (trace) fprintf(stderr, "sssp select %lld (%s): threshold %.3f queued %lld (local %lld) pending %lld, previous round relaxed %lld edges\n",
+                           (long long)selects, from_far ? "far" : "near", threshold, n_cur, n_local, pending, (long long)h_cnt[C_EDGES]);
         if (n_cur == 0)
         {
             if (!from_far)
@@ -577,26 +673,39 @@ extern "C" int vglb_sssp(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, i
                 continue;
             }
             if (pending == 0) break;
-            const uint32_t min_bits = 0xffffffffu - (uint32_t)h_cnt[C_MF];
+            const uint32_t min_bits = 0xffffffffu - (uint32_t)(part ? h_cnt[2 * C_COUNT] : h_cnt[C_MF]);
             float min_pending;
             memcpy(&min_pending, &min_bits, 4);
             threshold = fmaxf(threshold, min_pending) + delta; // nothing below the moved threshold: jump
             continue;
         }
         from_far = false;
-        // queue entries per warp: 32 when the frontier is large, fewer when it would leave SMs idle
-        int per_warp = 32;
-        while (per_warp > 1 && ceil_div64(n[1] + n[2], per_warp) < (int64_t)ctx->sm_count * 32) per_warp >>= 1;
-        const int64_t batches = ceil_div64(n[1], per_warp) + ceil_div64(n[2], per_warp);
-        const int64_t grid = (int64_t)n[0] + ceil_div64(batches, SSSP_THREADS / 32);
-        sssp_relax_flat_kernel<<<(unsigned)grid, SSSP_THREADS, 0, st>>>(g->d_out_ptr, g->d_out_adj, d_weights, cq, n[0], n[1], n[2], per_warp,
-                                                                       dist, near_bm, far_bm, tbits, d_cnt);
-        KERNEL_TRY();
-        ctx->launches++;
+        if (n_local > 0)
+        {
+            // queue entries per warp: 32 when the frontier is large, fewer when it would leave SMs idle
+            int per_warp = 32;
+            while (per_warp > 1 && ceil_div64(n[1] + n[2], per_warp) < (int64_t)ctx->sm_count * 32) per_warp >>= 1;
+            const int64_t batches = ceil_div64(n[1], per_warp) + ceil_div64(n[2], per_warp);
+            const int64_t grid = (int64_t)n[0] + ceil_div64(batches, SSSP_THREADS / 32);
+            sssp_relax_flat_kernel<<<(unsigned)grid, SSSP_THREADS, 0, st>>>(g->d_out_ptr, g->d_out_adj, d_weights, cq, n[0], n[1], n[2], per_warp,
+                                                                           dist, near_bm, far_bm, changed_bm, col0, vp, tbits, d_cnt);
+            KERNEL_TRY();
+            ctx->launches++;
+        }
+        if (part)
+        {
+            rc = vglb_comm_alltoall_async(comm, changed_bm, g->d_part_stage, (size_t)wslice * 4);
+            if (rc != VGLB_OK) return rc;
+            sssp_pull_kernel<<<select_grid, 256, 0, st>>>(g->d_part_stage, P, rank, wslice, col0, dist, d_peer_table, near_bm, far_bm, tbits, d_cnt);
+            KERNEL_TRY();
+            CUDA_TRY(cudaMemsetAsync(changed_bm, 0, words_full * 4, st));
+            ctx->launches++;
+        }
         rounds++;
-        tot_rows += n_cur;
-        tot_next += n_cur;
+        tot_rows += n_local;
+        tot_next += n_local;
     }
+    if (part && rows > 0) CUDA_TRY(cudaMemcpyAsync(d_dist, dist + col0, (size_t)rows * 4, cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(cudaEventRecord(ctx->ev_stop, st));
     CUDA_TRY(cudaEventSynchronize(ctx->ev_stop));
     if (stats)
@@ -608,9 +717,42 @@ extern "C" int vglb_sssp(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, i
         stats->iterations = rounds;
         stats->edges_inspected = tot_edges;
         stats->vertices_processed = tot_rows;
-        stats->frontier_bytes = 8 * tot_next + selects * (int64_t)words * 4 + far_selects * 4 * (int64_t)V; // queues, bitmap scans, far-pile distance reads
+        // queues, bitmap scans, far-pile distance reads; partitioned: + changed-bitmap slices sent / received / cleared
+        // and 32-byte sectors pulled from the peers
+        stats->frontier_bytes = 8 * tot_next + selects * (int64_t)words * 4 + far_selects * 4 * (int64_t)rows
+                                + (part ? rounds * (int64_t)words_full * 4 * 3 + 32 * tot_pulled : 0);
         stats->algorithmic_bytes = 12 * tot_edges + 24 * tot_rows + stats->frontier_bytes;
         stats->kernel_launches = ctx->launches - launches0;
     }
     return VGLB_OK;
+}
+
+extern "C" int vglb_sssp(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, int32_t source, float *d_dist,
+                         vglb_stats *stats)
+{
+    VGLB_REQUIRE(ctx != NULL && g != NULL && d_dist != NULL, "vglb_sssp: NULL argument");
+    VGLB_REQUIRE(d_weights != NULL || g->E == 0, "vglb_sssp: NULL weights");
+    VGLB_REQUIRE(source >= 0 && source < g->cols, "vglb_sssp: source out of range");
+    if (g->comm)
+    {
+        VGLB_REQUIRE(g->d_bwd != NULL, "vglb_sssp: partitioned graph without a column map");
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        if (!g->d_part_vec) CUDA_TRY(cudaMalloc(&g->d_part_vec, (size_t)g->cols * 4));
+        // map the peers' distance replicas once per graph; every rank must end up in the same mode
+        if (g->vec_peers_mapped == 0)
+        {
+            int ok = 1;
+            if (g->part_world > 8 || getenv("VGLB_SSSP_DENSE_EXCHANGE")) ok = 0;
+            else if (vglb_comm_ipc_map(g->comm, g->d_part_vec, (void **)g->d_vec_peer) != VGLB_OK) ok = 0;
+            int *d_ok = (int *)(ctx->d_counters + 62);
+            CUDA_TRY(cudaMemcpyAsync(d_ok, &ok, 4, cudaMemcpyHostToDevice, ctx->stream));
+            int rc = vglb_comm_allreduce_async(g->comm, d_ok, 1, VGLB_DT_I32, VGLB_OP_MIN);
+            if (rc != VGLB_OK) return rc;
+            CUDA_TRY(cudaMemcpyAsync(&ok, d_ok, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            g->vec_peers_mapped = ok ? 1 : -1;
+        }
+        if (g->vec_peers_mapped < 0) return sssp_partitioned_dense(ctx, g, d_weights, source, d_dist, stats);
+    }
+    return sssp_run(ctx, g, d_weights, source, d_dist, stats);
 }
