@@ -8,9 +8,10 @@
 // The unique fixed point is comp[v] = min sorted id over {v} U ancestors(v), the component minimum on
 // symmetric graphs, so any schedule of monotone hooks and jumps reaches bit-identical labels.
 //
-// B200 design: the hook is the lambda-generic all-active advance of include/vgl_b200/advance.cuh (the same template
-// the GraphAbstractionsB200 shim instantiates for user lambdas) with an atomicMin edge op — one launch covering all
-// degree tiers; hooks are applied in place, so a label travels many hops within one round (Gauss-Seidel), and the
+// B200 design: the hook is an all-active advance with an atomicMin edge op, one launch covering all degree tiers —
+// cc_hook_kernel below (load-balanced, several independent gathers per lane), or with VGLB_CC_GENERIC=1 the
+// lambda-generic template of include/vgl_b200/advance.cuh that the GraphAbstractionsB200 shim instantiates for user
+// lambdas (same labels, a third of the edge rate); hooks are applied in place, so a label travels many hops within one round (Gauss-Seidel), and the
 // whole jump loop of the reference collapses into ONE kernel that chases every vertex to its current root
 // (comp[x] <= x always holds, so the chase terminates and concurrent writes only shorten it). The convergence flag is
 // a device word read back once per round (the reference returns a reduce<int> to the host per round, :47-52).
@@ -21,6 +22,123 @@
 #include "common.cuh"
 #include "vgl_b200/advance.cuh"
 
+
+// ---- the hook as a load-balanced all-active advance specialised for min-label propagation ---------------------------
+// Same edge op as CcHookOp below (shiloach_vishkin.hpp:38-46), but scheduled for memory-level parallelism: the generic
+// per-row advance issues one dependent chain (index -> label -> atomic) per lane and step and reaches a third of the
+// PageRank sweep's edge rate. Here rows with >= 4096 edges get one CTA per CC_BIG_CHUNK edges, and a warp takes 32
+// consecutive smaller rows and walks the concatenation of their edge ranges (shuffle search over the degree prefix
+// sums, as in sssp.cu), CC_UNROLL edges per lane: the index loads, then the label gathers, are independent.
+#define CC_THREADS 256
+#define CC_UNROLL 4
+#define CC_BIG_CHUNK 8192
+
+__device__ __forceinline__ void cc_hook_one(int32_t *__restrict__ comp, int32_t cs, int32_t dst, int32_t cd, bool &changed)
+{
+    if (cs < cd)
+    {
+        if (atomicMin(&comp[dst], cs) > cs) changed = true;
+    }
+}
+
+__global__ void __launch_bounds__(CC_THREADS)
+cc_hook_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, int32_t n_big, int32_t big_chunks, int32_t rows_with_edges,
+               int32_t *__restrict__ comp, int32_t col0, int *changed_flag)
+{
+    // the convergence flag is written once per CTA: in the first round ~10^7 hooks succeed, and as many stores to one
+    // word serialise in L2
+    bool changed = false;
+    const unsigned FULL = 0xffffffffu;
+    const uint64_t pol = l2_policy_evict_first();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int big_blocks = n_big * big_chunks;
+    if ((int)blockIdx.x < big_blocks)
+    {
+        const int32_t row = blockIdx.x / big_chunks;
+        const int64_t s = ptr[row] + (int64_t)(blockIdx.x % big_chunks) * CC_BIG_CHUNK, e = min(ptr[row + 1], s + CC_BIG_CHUNK);
+        const int32_t cs = comp[col0 + row];
+        for (int64_t p0 = s + threadIdx.x; p0 < e; p0 += CC_THREADS * CC_UNROLL)
+        {
+            int32_t d[CC_UNROLL], cd[CC_UNROLL];
+#pragma unroll
+            for (int k = 0; k < CC_UNROLL; k++)
+            {
+                const int64_t p = p0 + (int64_t)k * CC_THREADS;
+                d[k] = p < e ? ld_stream_s32(adj + p, pol) : -1;
+            }
+#pragma unroll
+            for (int k = 0; k < CC_UNROLL; k++) cd[k] = d[k] >= 0 ? comp[d[k]] : INT_MIN;
+#pragma unroll
+            for (int k = 0; k < CC_UNROLL; k++) cc_hook_one(comp, cs, d[k], cd[k], changed);
+        }
+        if (__syncthreads_or(changed) && threadIdx.x == 0) *changed_flag = 1;
+        return;
+    }
+    const int32_t row = n_big + (((int)blockIdx.x - big_blocks) * (CC_THREADS / 32) + warp) * 32 + lane;
+    int64_t s = 0;
+    int deg = 0;
+    int32_t cs = 0;
+    if (row < rows_with_edges)
+    {
+        s = ptr[row];
+        deg = (int)(ptr[row + 1] - s);
+        cs = comp[col0 + row];
+    }
+    int incl = deg;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const int t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int excl = incl - deg;
+    const int total = __shfl_sync(FULL, incl, 31);
+    for (int base = 0; base < total; base += 32 * CC_UNROLL)
+    {
+        int32_t d[CC_UNROLL], csj[CC_UNROLL], cd[CC_UNROLL];
+#pragma unroll
+        for (int k = 0; k < CC_UNROLL; k++)
+        {
+            const int idx = base + k * 32 + lane;
+            int j = 0; // largest lane whose range starts at or before idx
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1)
+            {
+                const int ex = __shfl_sync(FULL, excl, j + step);
+                if (ex <= idx) j += step;
+            }
+            const int64_t sj = __shfl_sync(FULL, s, j);
+            const int exj = __shfl_sync(FULL, excl, j);
+            csj[k] = __shfl_sync(FULL, cs, j);
+            d[k] = idx < total ? ld_stream_s32(adj + sj + (idx - exj), pol) : -1;
+        }
+#pragma unroll
+        for (int k = 0; k < CC_UNROLL; k++) cd[k] = d[k] >= 0 ? comp[d[k]] : INT_MIN;
+#pragma unroll
+        for (int k = 0; k < CC_UNROLL; k++) cc_hook_one(comp, csj[k], d[k], cd[k], changed);
+    }
+    if (__syncthreads_or(changed) && threadIdx.x == 0) *changed_flag = 1;
+}
+
+static int cc_launch_hook(vglb_ctx *ctx, const vglb_graph *g, int32_t *comp, int32_t col0, int *d_changed)
+{
+    const int32_t n_big = g->tier_border[0], rows_with_edges = g->tier_border[VGLB_NUM_TIERS - 2];
+    const int big_chunks = (int)ceil_div64(g->max_degree > 0 ? g->max_degree : 1, CC_BIG_CHUNK);
+    const int64_t warps = ceil_div64(rows_with_edges - n_big, 32);
+    const int64_t grid = (int64_t)n_big * big_chunks + ceil_div64(warps, CC_THREADS / 32);
+    VGLB_REQUIRE(grid < 0x7fffffffLL, "vglb_cc: grid too large");
+    if (grid > 0)
+    {
+        cc_hook_kernel<<<(unsigned)grid, CC_THREADS, 0, ctx->stream>>>(g->d_out_ptr, g->d_out_adj, n_big, big_chunks, rows_with_edges, comp,
+                                                                      col0, d_changed);
+        KERNEL_TRY();
+        ctx->launches++;
+    }
+    return VGLB_OK;
+}
+
+// the same hook as a functor of the lambda-generic advance (include/vgl_b200/advance.cuh); VGLB_CC_GENERIC=1 routes the
+// hook through that template — the path an unmodified VGL algorithm source takes through the GraphAbstractionsB200 shim
 struct CcHookOp
 {
     int32_t *comp;
@@ -64,21 +182,6 @@ __global__ void cc_jump_kernel(int32_t *__restrict__ comp, int32_t V)
 // owns into its replica, one allreduce(min) per round combines the replicas (the reference exchanges the whole array
 // after its advance too, mpi_exchange.hpp:155-271), and every rank then runs the same pointer-jump over the whole
 // vector (deterministic: a chain's root never changes during the jump), so the replicas stay identical.
-struct CcHookPartOp
-{
-    int32_t *comp; // by column id
-    int *changed;
-    int32_t col0;
-    __device__ __forceinline__ void operator()(int src, int dst, int, long long, int) const
-    {
-        const int32_t cs = comp[col0 + src];
-        if (cs < comp[dst])
-        {
-            if (atomicMin(&comp[dst], cs) > cs) *changed = 1;
-        }
-    }
-};
-
 __device__ __forceinline__ int32_t cc_col_of_sorted(int32_t s, int32_t P, int32_t vp) { return (s % P) * vp + s / P; }
 
 __global__ void cc_part_init_kernel(int32_t *__restrict__ comp, int64_t cols, int32_t P, int32_t vp)
@@ -115,16 +218,6 @@ static int cc_partitioned(vglb_ctx *ctx, vglb_graph *g, int32_t *d_labels, vglb_
     if (!g->d_part_vec) CUDA_TRY(cudaMalloc(&g->d_part_vec, (size_t)g->cols * 4));
     int32_t *comp = (int32_t *)g->d_part_vec;
 
-    vglb::CsrView view;
-    view.ptr = g->d_out_ptr;
-    view.adj = g->d_out_adj;
-    view.V = rows;
-    for (int t = 0; t < VGLB_NUM_TIERS; t++) view.tier_border[t] = g->tier_border[t];
-    const vglb::AllActivePlan plan = vglb::plan_all_active(view);
-    VGLB_REQUIRE(plan.blocks < 0x7fffffffLL, "vglb_cc: grid too large");
-    CcHookPartOp hook{comp, d_changed, g->col_of_row0};
-    vglb::NoVertexOp none;
-
     CUDA_TRY(cudaEventRecord(ctx->ev_start, st));
     cc_part_init_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(comp, g->cols, P, vp);
     KERNEL_TRY();
@@ -134,12 +227,8 @@ static int cc_partitioned(vglb_ctx *ctx, vglb_graph *g, int32_t *d_labels, vglb_
     for (;;)
     {
         CUDA_TRY(cudaMemsetAsync(d_changed, 0, sizeof(int), st));
-        if (plan.blocks > 0)
-        {
-            vglb::advance_all_active_kernel<<<(unsigned)plan.blocks, vglb::kAdvThreads, 0, st>>>(view, plan, 0LL, hook, none, none, hook, none, none);
-            KERNEL_TRY();
-            ctx->launches++;
-        }
+        rc = cc_launch_hook(ctx, g, comp, g->col_of_row0, d_changed);
+        if (rc != VGLB_OK) return rc;
         hook_rounds++;
         rc = vglb_comm_allreduce_async(comm, comp, (size_t)g->cols, VGLB_DT_I32, VGLB_OP_MIN);
         if (rc != VGLB_OK) return rc;
@@ -191,6 +280,7 @@ extern "C" int vglb_cc(vglb_ctx *ctx, vglb_graph *g, int32_t *d_labels, vglb_sta
     VGLB_REQUIRE(plan.blocks < 0x7fffffffLL, "vglb_cc: grid too large");
     CcHookOp hook{d_labels, d_changed};
     vglb::NoVertexOp none;
+    const bool generic = getenv("VGLB_CC_GENERIC") != NULL;
 
     CUDA_TRY(cudaEventRecord(ctx->ev_start, st));
     cc_init_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_labels, V);
@@ -200,11 +290,19 @@ extern "C" int vglb_cc(vglb_ctx *ctx, vglb_graph *g, int32_t *d_labels, vglb_sta
     for (;;)
     {
         CUDA_TRY(cudaMemsetAsync(d_changed, 0, sizeof(int), st));
-        if (plan.blocks > 0)
+        if (generic)
         {
-            vglb::advance_all_active_kernel<<<(unsigned)plan.blocks, vglb::kAdvThreads, 0, st>>>(view, plan, 0LL, hook, none, none, hook, none, none);
-            KERNEL_TRY();
-            ctx->launches++;
+            if (plan.blocks > 0)
+            {
+                vglb::advance_all_active_kernel<<<(unsigned)plan.blocks, vglb::kAdvThreads, 0, st>>>(view, plan, 0LL, hook, none, none, hook, none, none);
+                KERNEL_TRY();
+                ctx->launches++;
+            }
+        }
+        else
+        {
+            int rc = cc_launch_hook(ctx, g, d_labels, 0, d_changed);
+            if (rc != VGLB_OK) return rc;
         }
         hook_rounds++;
         CUDA_TRY(cudaMemcpyAsync(h_changed, d_changed, sizeof(int), cudaMemcpyDeviceToHost, st));

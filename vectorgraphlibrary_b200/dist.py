@@ -130,7 +130,7 @@ class SingleGpuRunner:
         self.edges_per_step = self.g.E * self.iters_per_step
         self.out = ctx.empty(V, np.float32 if self.dtype == "f32" else np.int32)
         self.dominant_kernel = {"pr": "pr_sweep_kernel", "bfs": "bfs_td_kernel + bfs_bu_kernel (whole run)",
-                                "sssp": "sssp_relax_kernel (whole run)", "cc": "advance_all_active_kernel<CcHookOp> (whole run)"}[workload]
+                                "sssp": "sssp_relax_flat_kernel + sssp_select_kernel (whole run)", "cc": "cc_hook_kernel + cc_jump_kernel (whole run)"}[workload]
         self.weights = self.g.synthetic_weights(vgl.MASTER_SEED ^ 0x5555) if workload == "sssp" else None
         self.sources = None
         if workload in ("bfs", "sssp"):

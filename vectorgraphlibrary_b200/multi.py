@@ -71,7 +71,7 @@ class PartitionedRunner:
         self.edges_per_step = g.E_global * self.iters_per_step
         self.out = ctx.empty(max(1, g.V), np.float32 if self.dtype == "f32" else np.int32)
         self.dominant_kernel = {"pr": "pr_sweep_kernel", "bfs": "bfs_td_kernel + bfs_bu_kernel (whole run)",
-                                "sssp": "sssp_relax_kernel (whole run)", "cc": "advance_all_active_kernel<CcHookPartOp> (whole run)"}[workload]
+                                "sssp": "sssp_relax_flat_kernel + sssp_select_kernel (whole run)", "cc": "cc_hook_kernel + cc_jump_kernel (whole run)"}[workload]
         self.weights = g.synthetic_weights(vgl.MASTER_SEED ^ 0x5555) if workload == "sssp" else None
         self.sources = None
         if workload in ("bfs", "sssp"):
