@@ -211,6 +211,45 @@ def test_ragged_small_graph(vgl, ctx, oracle):
     G.free()
 
 
+def test_hubs_and_long_chain(vgl, ctx, oracle, monkeypatch):
+    """Rows on both sides of every tier border: two hubs with > 8192 out-edges (several CTA chunks per row), a 3000-vertex
+    chain (thousands of BFS levels / SSSP rounds with one-vertex frontiers) hanging off a hub, random filler. Also the
+    three SSSP schedules (reference's plain schedule, default near/far, a very fine threshold) must give the same bits."""
+    O = oracle
+    V = 1 << 15
+    rng = np.random.default_rng(17)
+    hub_a = np.full(20000, 5, np.int32)
+    hub_b = np.full(9000, 6, np.int32)
+    chain = np.arange(20000, 23000, dtype=np.int32)
+    src = np.concatenate([hub_a, hub_b, np.array([5], np.int32), chain[:-1], rng.integers(0, V, 60000).astype(np.int32)])
+    dst = np.concatenate([rng.integers(0, V, 20000).astype(np.int32), rng.integers(0, V, 9000).astype(np.int32),
+                          chain[:1], chain[1:], rng.integers(0, V, 60000).astype(np.int32)])
+    og = O.OracleGraph(V, src, dst)
+    G = vgl.Graph.from_edges(ctx, V, src, dst, vgl.GRAPH_WITH_INCOMING)
+    assert G.info.max_degree > 8192 and G.tiers()[1][0] >= 2
+    fwd = G.orig_to_sorted()
+    w = G.synthetic_weights(3)
+    for s in (5, 20000, 22990):
+        for dopt in (False, True):
+            lv, st = G.bfs(int(fwd[s]), direction_optimising=dopt)
+            assert np.array_equal(G.to_original(lv), og.bfs(s)[0]), (s, dopt)
+        ref = og.sssp(s, 3)[0].view(np.uint32)
+        for scale in ("0", "4", "0.05"):
+            monkeypatch.setenv("VGLB_SSSP_DELTA_SCALE", scale)
+            d, st = G.sssp(w, int(fwd[s]))
+            assert np.array_equal(G.to_original(d).view(np.uint32), ref), (s, scale)
+        monkeypatch.delenv("VGLB_SSSP_DELTA_SCALE")
+    lab, _ = G.cc()
+    assert np.array_equal(G.to_original(lab), og.cc()[0])
+    monkeypatch.setenv("VGLB_CC_GENERIC", "1")  # the hook through the lambda-generic advance template: same labels
+    lab2, _ = G.cc()
+    assert np.array_equal(lab2.to_numpy(), lab.to_numpy())
+    monkeypatch.delenv("VGLB_CC_GENERIC")
+    ranks, _ = G.pagerank(20)
+    assert O.rel_l1(G.to_original(ranks), og.pagerank_f64(20)) <= PR_TOL
+    G.free()
+
+
 def test_graph_without_edges(vgl, ctx):
     V = 40
     e = np.empty(0, np.int32)
