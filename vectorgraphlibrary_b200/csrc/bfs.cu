@@ -347,7 +347,7 @@ __global__ void bfs_no_in_edges_kernel(const int64_t *__restrict__ in_ptr, int32
 static int bfs_prepare_no_in_edges(vglb_ctx *ctx, vglb_graph *g)
 {
     if (g->d_scratch_i32 || !g->d_in_ptr) return VGLB_OK;
-    CUDA_TRY(cudaMalloc(&g->d_scratch_i32, (((size_t)g->V + 31) / 32 + 32) * 4));
+    CUDA_TRY(vglb_dev_alloc(&g->d_scratch_i32, (((size_t)g->V + 31) / 32 + 32) * 4));
     bfs_no_in_edges_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(g->d_in_ptr, g->V, (uint32_t *)g->d_scratch_i32);
     KERNEL_TRY();
     ctx->launches++;
@@ -516,9 +516,9 @@ static int bfs_partitioned(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t
     const int32_t wslice = vp / 32;
     const int64_t words = g->cols / 32, my = (int64_t)rank * wslice;
     for (int i = 0; i < 3; i++)
-        if (!g->d_part_bm[i]) CUDA_TRY(cudaMalloc(&g->d_part_bm[i], (size_t)(words + 32) * 4));
-    if (!g->d_part_stage) CUDA_TRY(cudaMalloc(&g->d_part_stage, (size_t)(words + 32) * 4));
-    if (!g->d_queue[0]) CUDA_TRY(cudaMalloc(&g->d_queue[0], ((size_t)vp + 3) * 4));
+        if (!g->d_part_bm[i]) CUDA_TRY(vglb_dev_alloc(&g->d_part_bm[i], (size_t)(words + 32) * 4));
+    if (!g->d_part_stage) CUDA_TRY(vglb_dev_alloc(&g->d_part_stage, (size_t)(words + 32) * 4));
+    if (!g->d_queue[0]) CUDA_TRY(vglb_dev_alloc(&g->d_queue[0], ((size_t)vp + 3) * 4));
     rc0 = bfs_prepare_no_in_edges(ctx, g);
     if (rc0 != VGLB_OK) return rc0;
     const int64_t launches0 = ctx->launches;
@@ -672,11 +672,11 @@ static int bfs_prepare(vglb_ctx *ctx, vglb_graph *g)
 {
     if (g->bfs_ready) return VGLB_OK;
     const size_t words = ((size_t)g->V + 31) / 32 + 32;
-    CUDA_TRY(cudaMalloc(&g->d_visited, words * 4));
-    CUDA_TRY(cudaMalloc(&g->d_front_bm[0], words * 4));
-    CUDA_TRY(cudaMalloc(&g->d_front_bm[1], words * 4));
-    CUDA_TRY(cudaMalloc(&g->d_queue[0], ((size_t)g->V + 3) * 4));
-    CUDA_TRY(cudaMalloc(&g->d_queue[1], ((size_t)g->V + 3) * 4));
+    CUDA_TRY(vglb_dev_alloc(&g->d_visited, words * 4));
+    CUDA_TRY(vglb_dev_alloc(&g->d_front_bm[0], words * 4));
+    CUDA_TRY(vglb_dev_alloc(&g->d_front_bm[1], words * 4));
+    CUDA_TRY(vglb_dev_alloc(&g->d_queue[0], ((size_t)g->V + 3) * 4));
+    CUDA_TRY(vglb_dev_alloc(&g->d_queue[1], ((size_t)g->V + 3) * 4));
     g->bfs_ready = 1;
     return bfs_prepare_no_in_edges(ctx, g);
 }

@@ -215,7 +215,7 @@ static int cc_partitioned(vglb_ctx *ctx, vglb_graph *g, int32_t *d_labels, vglb_
     cudaStream_t st = ctx->stream;
     int *d_changed = (int *)(ctx->d_counters + 40);
     int *h_changed = (int *)(ctx->h_counters + 40);
-    if (!g->d_part_vec) CUDA_TRY(cudaMalloc(&g->d_part_vec, (size_t)g->cols * 4));
+    if (!g->d_part_vec) CUDA_TRY(vglb_dev_alloc(&g->d_part_vec, (size_t)g->cols * 4));
     int32_t *comp = (int32_t *)g->d_part_vec;
 
     CUDA_TRY(cudaEventRecord(ctx->ev_start, st));

@@ -13,6 +13,17 @@
 
 void vglb_set_error(const char *fmt, ...);
 
+// cached device allocations (context.cu); drop-in for cudaMalloc / cudaFree inside the library
+cudaError_t vglb_dev_alloc_bytes(void **ptr, size_t bytes);
+void vglb_dev_free(void *ptr);
+void vglb_dev_mark_exported(void *ptr); // the block is visible to other processes (CUDA IPC): free it for real
+void vglb_dev_cache_release(void);
+template <class T>
+static inline cudaError_t vglb_dev_alloc(T **ptr, size_t bytes)
+{
+    return vglb_dev_alloc_bytes((void **)ptr, bytes);
+}
+
 // SAFE_CALL twin (cuda_error_handling.h:7-13): record the message and return an error code instead of throwing.
 #define CUDA_TRY(call)                                                                               \
     do                                                                                               \

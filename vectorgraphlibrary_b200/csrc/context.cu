@@ -20,6 +20,126 @@ void vglb_set_error(const char *fmt, ...)
 
 extern "C" const char *vglb_last_error(void) { return g_error; }
 
+// ---- device memory: a size-keyed cache in front of cudaMalloc / cudaFree ----------------------------------------------
+// cudaMalloc and cudaFree cost milliseconds each and cudaFree synchronises the device; a host program that moves a graph
+// to the device, runs an algorithm and drops it (the end-to-end path: VGL_Graph::move_to_device + vgl_page_rank) spent
+// more time in them than in its 20 sweeps. Freed blocks are kept and handed out again for requests of exactly the same
+// size (re-created graphs repeat their sizes); the cache is bounded and emptied when an allocation fails. Buffers exported
+// to other processes (CUDA IPC) are never recycled. (MemoryAPI::allocate_array / free_array, memory_API.hpp:3-15,95-101.)
+#include <map>
+#include <mutex>
+#include <unordered_map>
+#include <unordered_set>
+
+namespace
+{
+struct DeviceCache
+{
+    std::mutex mu;
+    std::unordered_map<void *, size_t> live;     // blocks handed out by vglb_dev_alloc
+    std::unordered_set<void *> exported;         // never recycled
+    std::multimap<size_t, void *> idle;          // freed blocks by size
+    size_t idle_bytes = 0;
+};
+DeviceCache &cache_of_current_device()
+{
+    static DeviceCache caches[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return caches[dev & 63];
+}
+size_t cache_limit()
+{
+    static size_t limit = 0;
+    if (!limit)
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) total_b = (size_t)16 << 30;
+        limit = total_b / 4;
+        if (const char *e = getenv("VGLB_DEVICE_CACHE_MB")) limit = (size_t)atoll(e) << 20;
+    }
+    return limit;
+}
+void cache_release_all(DeviceCache &C)
+{
+    for (auto &kv : C.idle) cudaFree(kv.second);
+    C.idle.clear();
+    C.idle_bytes = 0;
+}
+} // namespace
+
+cudaError_t vglb_dev_alloc_bytes(void **ptr, size_t bytes)
+{
+    if (bytes == 0) bytes = 16;
+    DeviceCache &C = cache_of_current_device();
+    std::lock_guard<std::mutex> lock(C.mu);
+    auto it = C.idle.find(bytes);
+    if (it != C.idle.end())
+    {
+        *ptr = it->second;
+        C.idle.erase(it);
+        C.idle_bytes -= bytes;
+        C.live[*ptr] = bytes;
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(ptr, bytes);
+    if (e != cudaSuccess && !C.idle.empty())
+    {
+        cudaGetLastError();
+        cache_release_all(C); // give the cached blocks back and try once more
+        e = cudaMalloc(ptr, bytes);
+    }
+    if (e == cudaSuccess) C.live[*ptr] = bytes;
+    return e;
+}
+
+void vglb_dev_free(void *ptr)
+{
+    if (!ptr) return;
+    DeviceCache &C = cache_of_current_device();
+    std::lock_guard<std::mutex> lock(C.mu);
+    auto it = C.live.find(ptr);
+    if (it == C.live.end())
+    {
+        cudaFree(ptr); // not ours (or another device's): plain free
+        return;
+    }
+    const size_t bytes = it->second;
+    C.live.erase(it);
+    if (C.exported.erase(ptr) || bytes > cache_limit())
+    {
+        cudaFree(ptr);
+        return;
+    }
+    // work enqueued on the context streams may still use the block; the next user is ordered behind it only on the same
+    // stream, so wait for the device before the block can be handed to anybody
+    cudaDeviceSynchronize();
+    C.idle.emplace(bytes, ptr);
+    C.idle_bytes += bytes;
+    while (C.idle_bytes > cache_limit() && !C.idle.empty())
+    {
+        auto big = std::prev(C.idle.end()); // largest first
+        cudaFree(big->second);
+        C.idle_bytes -= big->first;
+        C.idle.erase(big);
+    }
+}
+
+void vglb_dev_mark_exported(void *ptr)
+{
+    DeviceCache &C = cache_of_current_device();
+    std::lock_guard<std::mutex> lock(C.mu);
+    if (C.live.count(ptr)) C.exported.insert(ptr);
+}
+
+void vglb_dev_cache_release(void)
+{
+    DeviceCache &C = cache_of_current_device();
+    std::lock_guard<std::mutex> lock(C.mu);
+    cache_release_all(C);
+}
+
+
 extern "C" int vglb_device_count(void)
 {
     int n = 0;
@@ -52,7 +172,7 @@ extern "C" int vglb_init(int device, vglb_ctx **out_ctx)
     CUDA_TRY(cudaEventCreate(&ctx->ev_start));
     CUDA_TRY(cudaEventCreate(&ctx->ev_stop));
     CUDA_TRY(cudaMallocHost((void **)&ctx->h_counters, 64 * sizeof(int64_t)));
-    CUDA_TRY(cudaMalloc((void **)&ctx->d_counters, 64 * sizeof(int64_t)));
+    CUDA_TRY(vglb_dev_alloc((void **)&ctx->d_counters, 64 * sizeof(int64_t)));
     CUDA_TRY(cudaMemset(ctx->d_counters, 0, 64 * sizeof(int64_t)));
     ctx->flush_bytes = ctx->l2_bytes * 2 > (size_t)(256u << 20) ? ctx->l2_bytes * 2 : (size_t)(256u << 20);
     ctx->d_flush = NULL;
@@ -65,13 +185,14 @@ extern "C" int vglb_finalize(vglb_ctx *ctx)
     if (!ctx) return VGLB_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    if (ctx->d_flush) cudaFree(ctx->d_flush);
-    cudaFree(ctx->d_counters);
+    if (ctx->d_flush) vglb_dev_free(ctx->d_flush);
+    vglb_dev_free(ctx->d_counters);
     cudaFreeHost(ctx->h_counters);
     cudaEventDestroy(ctx->ev_start);
     cudaEventDestroy(ctx->ev_stop);
     cudaStreamDestroy(ctx->stream);
     free(ctx);
+    vglb_dev_cache_release(); // cached blocks of this device go back to the driver
     return VGLB_OK;
 }
 
@@ -88,7 +209,7 @@ extern "C" int vglb_malloc(vglb_ctx *ctx, size_t bytes, void **d_ptr)
 {
     VGLB_REQUIRE(ctx != NULL && d_ptr != NULL, "vglb_malloc: NULL argument");
     CUDA_TRY(cudaSetDevice(ctx->device));
-    cudaError_t e = cudaMalloc(d_ptr, bytes ? bytes : 16);
+    cudaError_t e = vglb_dev_alloc(d_ptr, bytes ? bytes : 16);
     if (e != cudaSuccess)
     {
         cudaGetLastError();
@@ -101,7 +222,7 @@ extern "C" int vglb_malloc(vglb_ctx *ctx, size_t bytes, void **d_ptr)
 extern "C" int vglb_free(vglb_ctx *ctx, void *d_ptr)
 {
     VGLB_REQUIRE(ctx != NULL, "vglb_free: ctx is NULL");
-    if (d_ptr) CUDA_TRY(cudaFree(d_ptr));
+    vglb_dev_free(d_ptr);
     return VGLB_OK;
 }
 
@@ -164,7 +285,7 @@ __global__ void flush_l2_kernel(uint4 *buf, size_t n16, uint32_t tag)
 extern "C" int vglb_flush_l2(vglb_ctx *ctx)
 {
     VGLB_REQUIRE(ctx != NULL, "vglb_flush_l2: ctx is NULL");
-    if (!ctx->d_flush) CUDA_TRY(cudaMalloc(&ctx->d_flush, ctx->flush_bytes));
+    if (!ctx->d_flush) CUDA_TRY(vglb_dev_alloc(&ctx->d_flush, ctx->flush_bytes));
     static uint32_t tag = 1;
     flush_l2_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((uint4 *)ctx->d_flush, ctx->flush_bytes / 16, tag++);
     KERNEL_TRY();

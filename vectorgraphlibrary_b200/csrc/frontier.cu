@@ -179,13 +179,13 @@ extern "C" int vglb_frontier_create(vglb_ctx *ctx, vglb_graph *g, vglb_frontier 
     f->g = g;
     const size_t words = ((size_t)g->V + 31) / 32 + 32;
     const size_t tiles = ((size_t)g->V + GNF_TILE - 1) / GNF_TILE + 1;
-    cudaError_t e = cudaMalloc(&f->d_bitmap, words * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&f->d_ids, ((size_t)g->V + 32) * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&f->d_tile_status, (tiles + G_COUNT) * 8);
+    cudaError_t e = vglb_dev_alloc(&f->d_bitmap, words * 4);
+    if (e == cudaSuccess) e = vglb_dev_alloc(&f->d_ids, ((size_t)g->V + 32) * 4);
+    if (e == cudaSuccess) e = vglb_dev_alloc(&f->d_tile_status, (tiles + G_COUNT) * 8);
     if (e != cudaSuccess)
     {
         cudaGetLastError();
-        cudaFree(f->d_bitmap); cudaFree(f->d_ids); cudaFree(f->d_tile_status);
+        vglb_dev_free(f->d_bitmap); vglb_dev_free(f->d_ids); vglb_dev_free(f->d_tile_status);
         free(f);
         vglb_set_error("vglb_frontier_create: cudaMalloc failed: %s", cudaGetErrorString(e));
         return VGLB_ENOMEM;
@@ -202,7 +202,7 @@ extern "C" int vglb_frontier_destroy(vglb_ctx *ctx, vglb_frontier *f)
     VGLB_REQUIRE(ctx != NULL, "vglb_frontier_destroy: ctx is NULL");
     if (!f) return VGLB_OK;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    cudaFree(f->d_bitmap); cudaFree(f->d_ids); cudaFree(f->d_tile_status);
+    vglb_dev_free(f->d_bitmap); vglb_dev_free(f->d_ids); vglb_dev_free(f->d_tile_status);
     free(f);
     return VGLB_OK;
 }

@@ -188,18 +188,18 @@ int vglb_graph_compute_tiers(vglb_ctx *ctx, vglb_graph *g)
 
 void vglb_graph_free_fields(vglb_graph *g)
 {
-    cudaFree(g->d_part_bm[0]); cudaFree(g->d_part_bm[1]); cudaFree(g->d_part_bm[2]); cudaFree(g->d_part_stage);
-    cudaFree(g->d_part_vec); cudaFree(g->d_part_prev);
+    vglb_dev_free(g->d_part_bm[0]); vglb_dev_free(g->d_part_bm[1]); vglb_dev_free(g->d_part_bm[2]); vglb_dev_free(g->d_part_stage);
+    vglb_dev_free(g->d_part_vec); vglb_dev_free(g->d_part_prev);
     for (int b = 0; b < 2; b++)
         for (int p = 0; p < 8; p++)
             if (g->d_pr_peer[b][p]) cudaIpcCloseMemHandle(g->d_pr_peer[b][p]);
     for (int p = 0; p < 8; p++)
         if (g->d_vec_peer[p] && p != g->part_rank) cudaIpcCloseMemHandle(g->d_vec_peer[p]);
-    cudaFree(g->d_out_ptr); cudaFree(g->d_out_adj); cudaFree(g->d_in_ptr); cudaFree(g->d_in_adj);
-    cudaFree(g->d_fwd); cudaFree(g->d_bwd); cudaFree(g->d_edge_order);
-    cudaFree(g->d_pr_inv); cudaFree(g->d_pr_contrib[0]); cudaFree(g->d_pr_contrib[1]); cudaFree(g->d_pr_dangling); cudaFree(g->d_pr_tasks); cudaFree(g->d_pr_piece_partial); cudaFree(g->d_pr_piece_count); cudaFree(g->d_pr_ve_adj); cudaFree(g->d_pr_ve_ptr);
-    cudaFree(g->d_visited); cudaFree(g->d_front_bm[0]); cudaFree(g->d_front_bm[1]);
-    cudaFree(g->d_queue[0]); cudaFree(g->d_queue[1]); cudaFree(g->d_scratch_i32);
+    vglb_dev_free(g->d_out_ptr); vglb_dev_free(g->d_out_adj); vglb_dev_free(g->d_in_ptr); vglb_dev_free(g->d_in_adj);
+    vglb_dev_free(g->d_fwd); vglb_dev_free(g->d_bwd); vglb_dev_free(g->d_edge_order);
+    vglb_dev_free(g->d_pr_inv); vglb_dev_free(g->d_pr_contrib[0]); vglb_dev_free(g->d_pr_contrib[1]); vglb_dev_free(g->d_pr_dangling); vglb_dev_free(g->d_pr_tasks); vglb_dev_free(g->d_pr_piece_partial); vglb_dev_free(g->d_pr_piece_count); vglb_dev_free(g->d_pr_ve_adj); vglb_dev_free(g->d_pr_ve_ptr);
+    vglb_dev_free(g->d_visited); vglb_dev_free(g->d_front_bm[0]); vglb_dev_free(g->d_front_bm[1]);
+    vglb_dev_free(g->d_queue[0]); vglb_dev_free(g->d_queue[1]); vglb_dev_free(g->d_scratch_i32);
 }
 
 extern "C" int vglb_graph_free(vglb_ctx *ctx, vglb_graph *g)
@@ -245,18 +245,18 @@ static int build_outgoing(vglb_ctx *ctx, int32_t V, int64_t E, const int32_t *d_
 {
     uint32_t *k0 = NULL, *k1 = NULL, *v0 = NULL, *v1 = NULL;
     void *tmp = NULL;
-    auto cleanup = [&]() { cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1); cudaFree(tmp); };
+    auto cleanup = [&]() { vglb_dev_free(k0); vglb_dev_free(k1); vglb_dev_free(v0); vglb_dev_free(v1); vglb_dev_free(tmp); };
     if (E == 0) return VGLB_OK;
     const size_t eb = (size_t)E * sizeof(uint32_t);
-    BUILD_CUDA(cudaMalloc(&k0, eb)); BUILD_CUDA(cudaMalloc(&k1, eb));
-    BUILD_CUDA(cudaMalloc(&v0, eb)); BUILD_CUDA(cudaMalloc(&v1, eb));
+    BUILD_CUDA(vglb_dev_alloc(&k0, eb)); BUILD_CUDA(vglb_dev_alloc(&k1, eb));
+    BUILD_CUDA(vglb_dev_alloc(&v0, eb)); BUILD_CUDA(vglb_dev_alloc(&v1, eb));
     const int grid = ctx->sm_count * 16;
     edge_keys_kernel<<<grid, 256, 0, ctx->stream>>>(d_src, d_fwd, E, k0, v0);
     BUILD_CUDA(cudaGetLastError());
     cub::DoubleBuffer<uint32_t> keys(k0, k1), vals(v0, v1);
     size_t tmp_bytes = 0;
     BUILD_CUDA(cub::DeviceRadixSort::SortPairs(NULL, tmp_bytes, keys, vals, E, 0, bits_for(V), ctx->stream));
-    BUILD_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+    BUILD_CUDA(vglb_dev_alloc(&tmp, tmp_bytes ? tmp_bytes : 16));
     BUILD_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, vals, E, 0, bits_for(V), ctx->stream));
     gather_adj_kernel<<<grid, 256, 0, ctx->stream>>>(vals.Current(), d_dst, d_fwd, E, d_adj, d_edge_order);
     BUILD_CUDA(cudaGetLastError());
@@ -275,15 +275,15 @@ static int build_incoming(vglb_ctx *ctx, int32_t V, int64_t E, const int32_t *d_
 {
     uint32_t *k0 = NULL, *k1 = NULL, *v1 = NULL;
     void *tmp = NULL;
-    auto cleanup = [&]() { cudaFree(k0); cudaFree(k1); cudaFree(v1); cudaFree(tmp); };
+    auto cleanup = [&]() { vglb_dev_free(k0); vglb_dev_free(k1); vglb_dev_free(v1); vglb_dev_free(tmp); };
     if (E == 0) return VGLB_OK;
     const size_t eb = (size_t)E * sizeof(uint32_t);
-    BUILD_CUDA(cudaMalloc(&k0, eb)); BUILD_CUDA(cudaMalloc(&k1, eb)); BUILD_CUDA(cudaMalloc(&v1, eb));
+    BUILD_CUDA(vglb_dev_alloc(&k0, eb)); BUILD_CUDA(vglb_dev_alloc(&k1, eb)); BUILD_CUDA(vglb_dev_alloc(&v1, eb));
     BUILD_CUDA(cudaMemcpyAsync(k0, d_out_adj, eb, cudaMemcpyDeviceToDevice, ctx->stream));
     cub::DoubleBuffer<uint32_t> keys(k0, k1), vals(d_row_of_pos, v1);
     size_t tmp_bytes = 0;
     BUILD_CUDA(cub::DeviceRadixSort::SortPairs(NULL, tmp_bytes, keys, vals, E, 0, bits_for(V), ctx->stream));
-    BUILD_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+    BUILD_CUDA(vglb_dev_alloc(&tmp, tmp_bytes ? tmp_bytes : 16));
     BUILD_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, vals, E, 0, bits_for(V), ctx->stream));
     BUILD_CUDA(cudaMemcpyAsync(d_in_adj, vals.Current(), eb, cudaMemcpyDeviceToDevice, ctx->stream));
     BUILD_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -308,8 +308,8 @@ extern "C" int vglb_graph_from_edges(vglb_ctx *ctx, int32_t V, int64_t E, const 
     void *tmp = NULL;
     int *d_bad = NULL;
     auto cleanup = [&]() {
-        cudaFree(d_src_own); cudaFree(d_dst_own); cudaFree(d_deg); cudaFree(dk0); cudaFree(dk1); cudaFree(dv0);
-        cudaFree(dv1); cudaFree(d_deg_sorted); cudaFree(tmp); cudaFree(d_bad); cudaFree(d_row_of_pos);
+        vglb_dev_free(d_src_own); vglb_dev_free(d_dst_own); vglb_dev_free(d_deg); vglb_dev_free(dk0); vglb_dev_free(dk1); vglb_dev_free(dv0);
+        vglb_dev_free(dv1); vglb_dev_free(d_deg_sorted); vglb_dev_free(tmp); vglb_dev_free(d_bad); vglb_dev_free(d_row_of_pos);
         vglb_graph_free_fields(g);
         free(g);
     };
@@ -317,8 +317,8 @@ extern "C" int vglb_graph_from_edges(vglb_ctx *ctx, int32_t V, int64_t E, const 
     const size_t eb = (size_t)(E ? E : 1) * sizeof(int32_t);
     if (!src_on_device)
     {
-        BUILD_CUDA(cudaMalloc(&d_src_own, eb));
-        BUILD_CUDA(cudaMalloc(&d_dst_own, eb));
+        BUILD_CUDA(vglb_dev_alloc(&d_src_own, eb));
+        BUILD_CUDA(vglb_dev_alloc(&d_dst_own, eb));
         BUILD_CUDA(cudaMemcpyAsync(d_src_own, src, (size_t)E * 4, cudaMemcpyHostToDevice, ctx->stream));
         BUILD_CUDA(cudaMemcpyAsync(d_dst_own, dst, (size_t)E * 4, cudaMemcpyHostToDevice, ctx->stream));
         d_src = d_src_own;
@@ -328,8 +328,8 @@ extern "C" int vglb_graph_from_edges(vglb_ctx *ctx, int32_t V, int64_t E, const 
     const unsigned vgrid = (unsigned)ceil_div64((int64_t)V + 1, 256);
 
     // 1. out-degree histogram (extract_connection_count)
-    BUILD_CUDA(cudaMalloc(&d_deg, (size_t)V * 4));
-    BUILD_CUDA(cudaMalloc(&d_bad, 4));
+    BUILD_CUDA(vglb_dev_alloc(&d_deg, (size_t)V * 4));
+    BUILD_CUDA(vglb_dev_alloc(&d_bad, 4));
     BUILD_CUDA(cudaMemsetAsync(d_deg, 0, (size_t)V * 4, ctx->stream));
     BUILD_CUDA(cudaMemsetAsync(d_bad, 0, 4, ctx->stream));
     if (E)
@@ -349,40 +349,40 @@ extern "C" int vglb_graph_from_edges(vglb_ctx *ctx, int32_t V, int64_t E, const 
         return VGLB_EINVAL;
     }
     // 2. stable sort of vertex ids by degree descending (sort_vertices_by_degree)
-    BUILD_CUDA(cudaMalloc(&dk0, (size_t)V * 4)); BUILD_CUDA(cudaMalloc(&dk1, (size_t)V * 4));
-    BUILD_CUDA(cudaMalloc(&dv0, (size_t)V * 4)); BUILD_CUDA(cudaMalloc(&dv1, (size_t)V * 4));
+    BUILD_CUDA(vglb_dev_alloc(&dk0, (size_t)V * 4)); BUILD_CUDA(vglb_dev_alloc(&dk1, (size_t)V * 4));
+    BUILD_CUDA(vglb_dev_alloc(&dv0, (size_t)V * 4)); BUILD_CUDA(vglb_dev_alloc(&dv1, (size_t)V * 4));
     degree_sort_keys_kernel<<<vgrid, 256, 0, ctx->stream>>>(d_deg, V, dk0, dv0);
     BUILD_CUDA(cudaGetLastError());
     {
         cub::DoubleBuffer<uint32_t> keys(dk0, dk1), vals(dv0, dv1);
         size_t tmp_bytes = 0;
         BUILD_CUDA(cub::DeviceRadixSort::SortPairs(NULL, tmp_bytes, keys, vals, V, 0, 32, ctx->stream));
-        BUILD_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+        BUILD_CUDA(vglb_dev_alloc(&tmp, tmp_bytes ? tmp_bytes : 16));
         BUILD_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, vals, V, 0, 32, ctx->stream));
-        BUILD_CUDA(cudaMalloc(&g->d_fwd, (size_t)V * 4));
-        BUILD_CUDA(cudaMalloc(&g->d_bwd, (size_t)V * 4));
-        BUILD_CUDA(cudaMalloc(&d_deg_sorted, ((size_t)V + 1) * 8));
+        BUILD_CUDA(vglb_dev_alloc(&g->d_fwd, (size_t)V * 4));
+        BUILD_CUDA(vglb_dev_alloc(&g->d_bwd, (size_t)V * 4));
+        BUILD_CUDA(vglb_dev_alloc(&d_deg_sorted, ((size_t)V + 1) * 8));
         conversions_kernel<<<vgrid, 256, 0, ctx->stream>>>(vals.Current(), d_deg, V, g->d_fwd, g->d_bwd, d_deg_sorted);
         BUILD_CUDA(cudaGetLastError());
         BUILD_CUDA(cudaStreamSynchronize(ctx->stream));
-        cudaFree(tmp); tmp = NULL;
+        vglb_dev_free(tmp); tmp = NULL;
     }
-    cudaFree(dk0); cudaFree(dk1); cudaFree(dv0); cudaFree(dv1);
+    vglb_dev_free(dk0); vglb_dev_free(dk1); vglb_dev_free(dv0); vglb_dev_free(dv1);
     dk0 = dk1 = dv0 = dv1 = NULL;
     // 3. row pointers (construct_CSR)
-    BUILD_CUDA(cudaMalloc(&g->d_out_ptr, ((size_t)V + 2) * 8));
+    BUILD_CUDA(vglb_dev_alloc(&g->d_out_ptr, ((size_t)V + 2) * 8));
     {
         size_t tmp_bytes = 0;
         BUILD_CUDA(cub::DeviceScan::ExclusiveSum(NULL, tmp_bytes, d_deg_sorted, g->d_out_ptr, V + 1, ctx->stream));
-        BUILD_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+        BUILD_CUDA(vglb_dev_alloc(&tmp, tmp_bytes ? tmp_bytes : 16));
         BUILD_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_deg_sorted, g->d_out_ptr, V + 1, ctx->stream));
         BUILD_CUDA(cudaStreamSynchronize(ctx->stream));
-        cudaFree(tmp); tmp = NULL;
+        vglb_dev_free(tmp); tmp = NULL;
     }
     // 4. edges: stable sort by new src id, adjacency in new ids (renumber + preprocess_into_csr_based)
-    BUILD_CUDA(cudaMalloc(&g->d_out_adj, eb + 16));
-    if (flags & VGLB_GRAPH_WITH_EDGE_ORDER) BUILD_CUDA(cudaMalloc(&g->d_edge_order, (size_t)(E ? E : 1) * 8));
-    if ((flags & VGLB_GRAPH_WITH_INCOMING) && E) BUILD_CUDA(cudaMalloc(&d_row_of_pos, eb));
+    BUILD_CUDA(vglb_dev_alloc(&g->d_out_adj, eb + 16));
+    if (flags & VGLB_GRAPH_WITH_EDGE_ORDER) BUILD_CUDA(vglb_dev_alloc(&g->d_edge_order, (size_t)(E ? E : 1) * 8));
+    if ((flags & VGLB_GRAPH_WITH_INCOMING) && E) BUILD_CUDA(vglb_dev_alloc(&d_row_of_pos, eb));
     BUILD_TRY(build_outgoing(ctx, V, E, d_src, d_dst, g->d_fwd, g->d_out_adj, g->d_edge_order, d_row_of_pos));
     // 5. incoming CSR on the same numbering
     if (flags & VGLB_GRAPH_WITH_INCOMING)
@@ -393,20 +393,20 @@ extern "C" int vglb_graph_from_edges(vglb_ctx *ctx, int32_t V, int64_t E, const 
             indegree_sorted_kernel<<<grid, 256, 0, ctx->stream>>>(d_dst, g->d_fwd, E, (unsigned long long *)d_deg_sorted);
             BUILD_CUDA(cudaGetLastError());
         }
-        BUILD_CUDA(cudaMalloc(&g->d_in_ptr, ((size_t)V + 2) * 8));
+        BUILD_CUDA(vglb_dev_alloc(&g->d_in_ptr, ((size_t)V + 2) * 8));
         size_t tmp_bytes = 0;
         BUILD_CUDA(cub::DeviceScan::ExclusiveSum(NULL, tmp_bytes, d_deg_sorted, g->d_in_ptr, V + 1, ctx->stream));
-        BUILD_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+        BUILD_CUDA(vglb_dev_alloc(&tmp, tmp_bytes ? tmp_bytes : 16));
         BUILD_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_deg_sorted, g->d_in_ptr, V + 1, ctx->stream));
         BUILD_CUDA(cudaStreamSynchronize(ctx->stream));
-        cudaFree(tmp); tmp = NULL;
-        BUILD_CUDA(cudaMalloc(&g->d_in_adj, eb + 16));
+        vglb_dev_free(tmp); tmp = NULL;
+        BUILD_CUDA(vglb_dev_alloc(&g->d_in_adj, eb + 16));
         BUILD_TRY(build_incoming(ctx, V, E, g->d_out_adj, d_row_of_pos, g->d_in_adj));
     }
     BUILD_TRY(vglb_graph_compute_tiers(ctx, g));
     vglb_graph_set_unpartitioned(g);
-    cudaFree(d_src_own); cudaFree(d_dst_own); cudaFree(d_deg); cudaFree(d_deg_sorted); cudaFree(d_bad);
-    cudaFree(d_row_of_pos);
+    vglb_dev_free(d_src_own); vglb_dev_free(d_dst_own); vglb_dev_free(d_deg); vglb_dev_free(d_deg_sorted); vglb_dev_free(d_bad);
+    vglb_dev_free(d_row_of_pos);
     *out_graph = g;
     return VGLB_OK;
 }
@@ -425,19 +425,19 @@ extern "C" int vglb_graph_from_csr(vglb_ctx *ctx, int32_t V, int64_t E, const in
     g->E = E;
     auto cleanup = [&]() { vglb_graph_free_fields(g); free(g); };
     const size_t eb = (size_t)(E ? E : 1) * 4;
-    BUILD_CUDA(cudaMalloc(&g->d_out_ptr, ((size_t)V + 2) * 8));
-    BUILD_CUDA(cudaMalloc(&g->d_out_adj, eb + 16));
+    BUILD_CUDA(vglb_dev_alloc(&g->d_out_ptr, ((size_t)V + 2) * 8));
+    BUILD_CUDA(vglb_dev_alloc(&g->d_out_adj, eb + 16));
     BUILD_CUDA(cudaMemcpyAsync(g->d_out_ptr, h_out_ptr, ((size_t)V + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
     BUILD_CUDA(cudaMemcpyAsync(g->d_out_adj, h_out_adj, (size_t)E * 4, cudaMemcpyHostToDevice, ctx->stream));
     if (h_in_ptr)
     {
-        BUILD_CUDA(cudaMalloc(&g->d_in_ptr, ((size_t)V + 2) * 8));
-        BUILD_CUDA(cudaMalloc(&g->d_in_adj, eb + 16));
+        BUILD_CUDA(vglb_dev_alloc(&g->d_in_ptr, ((size_t)V + 2) * 8));
+        BUILD_CUDA(vglb_dev_alloc(&g->d_in_adj, eb + 16));
         BUILD_CUDA(cudaMemcpyAsync(g->d_in_ptr, h_in_ptr, ((size_t)V + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
         BUILD_CUDA(cudaMemcpyAsync(g->d_in_adj, h_in_adj, (size_t)E * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
-    BUILD_CUDA(cudaMalloc(&g->d_fwd, (size_t)V * 4));
-    BUILD_CUDA(cudaMalloc(&g->d_bwd, (size_t)V * 4));
+    BUILD_CUDA(vglb_dev_alloc(&g->d_fwd, (size_t)V * 4));
+    BUILD_CUDA(vglb_dev_alloc(&g->d_bwd, (size_t)V * 4));
     const unsigned vgrid = (unsigned)ceil_div64(V, 256);
     if (h_orig_to_sorted)
         BUILD_CUDA(cudaMemcpyAsync(g->d_fwd, h_orig_to_sorted, (size_t)V * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -544,7 +544,7 @@ extern "C" int vglb_varray_reorder_u32(vglb_ctx *ctx, vglb_graph *g, const uint3
             return VGLB_OK;
         }
         uint32_t *full = NULL;
-        CUDA_TRY(cudaMalloc(&full, (size_t)g->cols * 4));
+        CUDA_TRY(vglb_dev_alloc(&full, (size_t)g->cols * 4));
         CUDA_TRY(cudaMemsetAsync(full + g->col_of_row0, 0, (size_t)g->vp * 4, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(full + g->col_of_row0, d_in, (size_t)g->V * 4, cudaMemcpyDeviceToDevice, ctx->stream));
         int rc = vglb_comm_allgather_async(g->comm, full, (size_t)g->vp * 4);
@@ -554,7 +554,7 @@ extern "C" int vglb_varray_reorder_u32(vglb_ctx *ctx, vglb_graph *g, const uint3
             if (cudaGetLastError() != cudaSuccess) rc = VGLB_ECUDA;
         }
         cudaStreamSynchronize(ctx->stream);
-        cudaFree(full);
+        vglb_dev_free(full);
         ctx->launches++;
         return rc;
     }

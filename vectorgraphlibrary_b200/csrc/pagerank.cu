@@ -41,6 +41,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <time.h>
+
 #include <vector>
 
 #include <cub/device/device_scan.cuh>
@@ -443,12 +445,12 @@ static int pr_build_tasks(vglb_ctx *ctx, vglb_graph *g)
     g->pr_ntasks = (int32_t)tasks.size();
     if (!tasks.empty())
     {
-        CUDA_TRY(cudaMalloc(&g->d_pr_tasks, tasks.size() * sizeof(PrTask)));
+        CUDA_TRY(vglb_dev_alloc(&g->d_pr_tasks, tasks.size() * sizeof(PrTask)));
         CUDA_TRY(cudaMemcpyAsync(g->d_pr_tasks, tasks.data(), tasks.size() * sizeof(PrTask), cudaMemcpyHostToDevice, ctx->stream));
     }
-    CUDA_TRY(cudaMalloc(&g->d_pr_piece_partial, (size_t)(slots > 0 ? slots : 1) * 4));
+    CUDA_TRY(vglb_dev_alloc(&g->d_pr_piece_partial, (size_t)(slots > 0 ? slots : 1) * 4));
     const size_t counters = (size_t)(g->tier_border[0] > 0 ? g->tier_border[0] : 1);
-    CUDA_TRY(cudaMalloc(&g->d_pr_piece_count, counters * 4));
+    CUDA_TRY(vglb_dev_alloc(&g->d_pr_piece_count, counters * 4));
     CUDA_TRY(cudaMemsetAsync(g->d_pr_piece_count, 0, counters * 4, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return VGLB_OK;
@@ -491,22 +493,22 @@ static int pr_build_tail_copy(vglb_ctx *ctx, vglb_graph *g)
     const int32_t tail_first = g->tier_border[1], zero_first = g->tier_border[VGLB_NUM_TIERS - 2];
     const int32_t segments = (int32_t)ceil_div64(zero_first - tail_first, 32);
     g->pr_ve_segments = segments;
-    CUDA_TRY(cudaMalloc(&g->d_pr_ve_ptr, ((size_t)segments + 2) * 8));
+    CUDA_TRY(vglb_dev_alloc(&g->d_pr_ve_ptr, ((size_t)segments + 2) * 8));
     int64_t *d_len = NULL;
-    CUDA_TRY(cudaMalloc(&d_len, ((size_t)segments + 2) * 8));
+    CUDA_TRY(vglb_dev_alloc(&d_len, ((size_t)segments + 2) * 8));
     pr_ve_seglen_kernel<<<(unsigned)ceil_div64(segments + 1, 256), 256, 0, ctx->stream>>>(g->d_out_ptr, tail_first, segments, d_len);
     KERNEL_TRY();
     size_t tmp_bytes = 0;
     void *tmp = NULL;
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(NULL, tmp_bytes, d_len, g->d_pr_ve_ptr, segments + 1, ctx->stream));
-    CUDA_TRY(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+    CUDA_TRY(vglb_dev_alloc(&tmp, tmp_bytes ? tmp_bytes : 16));
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_len, g->d_pr_ve_ptr, segments + 1, ctx->stream));
     int64_t total = 0;
     CUDA_TRY(cudaMemcpyAsync(&total, g->d_pr_ve_ptr + segments, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    cudaFree(tmp);
-    cudaFree(d_len);
-    CUDA_TRY(cudaMalloc(&g->d_pr_ve_adj, (size_t)(total > 0 ? total : 1) * 4));
+    vglb_dev_free(tmp);
+    vglb_dev_free(d_len);
+    CUDA_TRY(vglb_dev_alloc(&g->d_pr_ve_adj, (size_t)(total > 0 ? total : 1) * 4));
     if (segments > 0)
     {
         pr_ve_fill_kernel<<<(unsigned)ceil_div64((int64_t)segments * 32, 256), 256, 0, ctx->stream>>>(
@@ -517,26 +519,44 @@ static int pr_build_tail_copy(vglb_ctx *ctx, vglb_graph *g)
     return VGLB_OK;
 }
 
+static double pr_now()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
 int vglb_pr_prepare(vglb_ctx *ctx, vglb_graph *g, int iters)
 {
+    const bool trace = getenv("VGLB_PR_TRACE") != NULL; // developer aid: time of every one-off preparation stage
+    double t_last = 0.0;
+    auto lap = [&](const char *what) {
+        if (!trace) return;
+        cudaStreamSynchronize(ctx->stream);
+        const double now = pr_now();
+        if (t_last > 0.0) fprintf(stderr, "pr prepare: %-28s %.2f ms\n", what, (now - t_last) * 1e3);
+        t_last = now;
+    };
+    lap("start");
     if (!g->d_pr_contrib[0])
     {
         // the gathered vector is indexed by column id: the whole (replicated) vector on a partitioned graph
-        CUDA_TRY(cudaMalloc(&g->d_pr_contrib[0], (size_t)g->cols * 4));
-        CUDA_TRY(cudaMalloc(&g->d_pr_contrib[1], (size_t)g->cols * 4));
+        CUDA_TRY(vglb_dev_alloc(&g->d_pr_contrib[0], (size_t)g->cols * 4));
+        CUDA_TRY(vglb_dev_alloc(&g->d_pr_contrib[1], (size_t)g->cols * 4));
         CUDA_TRY(cudaMemsetAsync(g->d_pr_contrib[0], 0, (size_t)g->cols * 4, ctx->stream));
         CUDA_TRY(cudaMemsetAsync(g->d_pr_contrib[1], 0, (size_t)g->cols * 4, ctx->stream));
     }
+    lap("contribution vectors");
     if (!g->d_pr_inv && g->comm) // part uploaded by vglb_graph_from_csr_partitioned: count columns locally, allreduce(sum)
     {
         int32_t *d_indeg = NULL;
-        CUDA_TRY(cudaMalloc(&d_indeg, (size_t)g->cols * 4));
+        CUDA_TRY(vglb_dev_alloc(&d_indeg, (size_t)g->cols * 4));
         CUDA_TRY(cudaMemsetAsync(d_indeg, 0, (size_t)g->cols * 4, ctx->stream));
         pr_part_indegree_kernel<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(g->d_out_ptr, g->d_out_adj, g->V, g->col_of_row0, d_indeg);
         KERNEL_TRY();
         int rc = vglb_comm_allreduce_async(g->comm, d_indeg, (size_t)g->cols, VGLB_DT_I32, VGLB_OP_SUM);
-        if (rc != VGLB_OK) { cudaFree(d_indeg); return rc; }
-        CUDA_TRY(cudaMalloc(&g->d_pr_inv, (size_t)g->vp * 4));
+        if (rc != VGLB_OK) { vglb_dev_free(d_indeg); return rc; }
+        CUDA_TRY(vglb_dev_alloc(&g->d_pr_inv, (size_t)g->vp * 4));
         CUDA_TRY(cudaMemsetAsync(g->d_pr_inv, 0, (size_t)g->vp * 4, ctx->stream));
         if (g->V > 0)
         {
@@ -545,33 +565,36 @@ int vglb_pr_prepare(vglb_ctx *ctx, vglb_graph *g, int iters)
         }
         ctx->launches += 2;
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        cudaFree(d_indeg);
+        vglb_dev_free(d_indeg);
     }
     if (!g->d_pr_inv) // (the partitioned build fills it from its degree pass)
     {
         int32_t *d_indeg = NULL;
-        CUDA_TRY(cudaMalloc(&d_indeg, (size_t)g->V * 4));
+        CUDA_TRY(vglb_dev_alloc(&d_indeg, (size_t)g->V * 4));
         int rc = vglb_graph_indegree_noloops(ctx, g, d_indeg);
-        if (rc != VGLB_OK) { cudaFree(d_indeg); return rc; }
-        CUDA_TRY(cudaMalloc(&g->d_pr_inv, (size_t)g->V * 4));
+        if (rc != VGLB_OK) { vglb_dev_free(d_indeg); return rc; }
+        CUDA_TRY(vglb_dev_alloc(&g->d_pr_inv, (size_t)g->V * 4));
         pr_inverse_degree_kernel<<<(unsigned)ceil_div64(g->V, 256), 256, 0, ctx->stream>>>(d_indeg, g->V, g->d_pr_inv);
         KERNEL_TRY();
         ctx->launches++;
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        cudaFree(d_indeg);
+        vglb_dev_free(d_indeg);
     }
+    lap("inverse in-degrees");
     if (!g->d_pr_piece_count)
     {
         int rc = pr_build_tasks(ctx, g);
         if (rc != VGLB_OK) return rc;
+        lap("warp tasks of the heavy rows");
         rc = pr_build_tail_copy(ctx, g);
         if (rc != VGLB_OK) return rc;
+        lap("padded copy of the tail rows");
     }
     if (g->pr_dangling_slots < iters + 1)
     {
-        cudaFree(g->d_pr_dangling);
+        vglb_dev_free(g->d_pr_dangling);
         g->d_pr_dangling = NULL;
-        CUDA_TRY(cudaMalloc(&g->d_pr_dangling, (size_t)(iters + 1) * sizeof(double)));
+        CUDA_TRY(vglb_dev_alloc(&g->d_pr_dangling, (size_t)(iters + 1) * sizeof(double)));
         g->pr_dangling_slots = iters + 1;
     }
     return VGLB_OK;
@@ -752,17 +775,19 @@ extern "C" int vglb_graph_set_exchange(vglb_ctx *ctx, vglb_graph *g, int mode)
         const int P = g->part_world, rank = g->part_rank;
         const size_t hb = sizeof(cudaIpcMemHandle_t);
         cudaIpcMemHandle_t mine[2];
+        vglb_dev_mark_exported(g->d_pr_contrib[0]);
+        vglb_dev_mark_exported(g->d_pr_contrib[1]);
         CUDA_TRY(cudaIpcGetMemHandle(&mine[0], g->d_pr_contrib[0]));
         CUDA_TRY(cudaIpcGetMemHandle(&mine[1], g->d_pr_contrib[1]));
         char *d_all = NULL;
-        CUDA_TRY(cudaMalloc(&d_all, (size_t)P * 2 * hb));
+        CUDA_TRY(vglb_dev_alloc(&d_all, (size_t)P * 2 * hb));
         CUDA_TRY(cudaMemcpyAsync(d_all + (size_t)rank * 2 * hb, mine, 2 * hb, cudaMemcpyHostToDevice, ctx->stream));
         rc = vglb_comm_allgather_async(g->comm, d_all, 2 * hb);
-        if (rc != VGLB_OK) { cudaFree(d_all); return rc; }
+        if (rc != VGLB_OK) { vglb_dev_free(d_all); return rc; }
         cudaIpcMemHandle_t all[2 * PR_MAX_PEERS];
         CUDA_TRY(cudaMemcpyAsync(all, d_all, (size_t)P * 2 * hb, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        cudaFree(d_all);
+        vglb_dev_free(d_all);
         for (int p = 0; p < P; p++)
         {
             if (p == rank) continue;

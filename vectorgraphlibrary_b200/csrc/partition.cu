@@ -218,16 +218,17 @@ int vglb_comm_ipc_map(vglb_comm *comm, void *d_local, void **peers)
     const int P = comm->world, rank = comm->rank;
     const size_t hb = sizeof(cudaIpcMemHandle_t);
     cudaIpcMemHandle_t mine;
+    vglb_dev_mark_exported(d_local);
     CUDA_TRY(cudaIpcGetMemHandle(&mine, d_local));
     char *d_all = NULL;
-    CUDA_TRY(cudaMalloc(&d_all, (size_t)P * hb));
+    CUDA_TRY(vglb_dev_alloc(&d_all, (size_t)P * hb));
     CUDA_TRY(cudaMemcpyAsync(d_all + (size_t)rank * hb, &mine, hb, cudaMemcpyHostToDevice, ctx->stream));
     int rc = vglb_comm_allgather_async(comm, d_all, hb);
-    if (rc != VGLB_OK) { cudaFree(d_all); return rc; }
+    if (rc != VGLB_OK) { vglb_dev_free(d_all); return rc; }
     cudaIpcMemHandle_t all[64];
     CUDA_TRY(cudaMemcpyAsync(all, d_all, (size_t)P * hb, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_all);
+    vglb_dev_free(d_all);
     for (int q = 0; q < P; q++)
     {
         if (q == rank) { peers[q] = d_local; continue; }
@@ -499,9 +500,9 @@ static int build_partitioned(vglb_ctx *ctx, vglb_comm *comm, int32_t V, const Ed
     void *tmp = NULL;
     int *d_bad = NULL;
     auto cleanup = [&]() {
-        cudaFree(buf_a); cudaFree(buf_b); cudaFree(d_deg_out); cudaFree(d_deg_in); cudaFree(d_deg_nl); cudaFree(k0);
-        cudaFree(k1); cudaFree(v0); cudaFree(v1); cudaFree(keys0); cudaFree(keys1); cudaFree(d_rowcnt); cudaFree(d_misc);
-        cudaFree(tmp); cudaFree(d_bad);
+        vglb_dev_free(buf_a); vglb_dev_free(buf_b); vglb_dev_free(d_deg_out); vglb_dev_free(d_deg_in); vglb_dev_free(d_deg_nl); vglb_dev_free(k0);
+        vglb_dev_free(k1); vglb_dev_free(v0); vglb_dev_free(v1); vglb_dev_free(keys0); vglb_dev_free(keys1); vglb_dev_free(d_rowcnt); vglb_dev_free(d_misc);
+        vglb_dev_free(tmp); vglb_dev_free(d_bad);
         if (g) { vglb_graph_free_fields(g); free(g); }
     };
     const int grid = ctx->sm_count * 16;
@@ -509,15 +510,15 @@ static int build_partitioned(vglb_ctx *ctx, vglb_comm *comm, int32_t V, const Ed
     const int64_t chunk = S.edges < kChunkEdges ? (S.edges > 0 ? S.edges : 1) : kChunkEdges;
     if (S.mode != 1)
     {
-        PBUILD_CUDA(cudaMalloc(&buf_a, (size_t)chunk * 4));
-        PBUILD_CUDA(cudaMalloc(&buf_b, (size_t)chunk * 4));
+        PBUILD_CUDA(vglb_dev_alloc(&buf_a, (size_t)chunk * 4));
+        PBUILD_CUDA(vglb_dev_alloc(&buf_b, (size_t)chunk * 4));
     }
     // pass 1: degrees of every vertex (identical on every rank)
-    PBUILD_CUDA(cudaMalloc(&d_deg_out, (size_t)V * 4));
-    PBUILD_CUDA(cudaMalloc(&d_deg_in, (size_t)V * 4));
-    PBUILD_CUDA(cudaMalloc(&d_deg_nl, (size_t)V * 4));
-    PBUILD_CUDA(cudaMalloc(&d_bad, 4));
-    PBUILD_CUDA(cudaMalloc(&d_misc, 8 * 8));
+    PBUILD_CUDA(vglb_dev_alloc(&d_deg_out, (size_t)V * 4));
+    PBUILD_CUDA(vglb_dev_alloc(&d_deg_in, (size_t)V * 4));
+    PBUILD_CUDA(vglb_dev_alloc(&d_deg_nl, (size_t)V * 4));
+    PBUILD_CUDA(vglb_dev_alloc(&d_bad, 4));
+    PBUILD_CUDA(vglb_dev_alloc(&d_misc, 8 * 8));
     PBUILD_CUDA(cudaMemsetAsync(d_deg_out, 0, (size_t)V * 4, st));
     PBUILD_CUDA(cudaMemsetAsync(d_deg_in, 0, (size_t)V * 4, st));
     PBUILD_CUDA(cudaMemsetAsync(d_deg_nl, 0, (size_t)V * 4, st));
@@ -543,8 +544,8 @@ static int build_partitioned(vglb_ctx *ctx, vglb_comm *comm, int32_t V, const Ed
         return VGLB_EINVAL;
     }
     // the reference's numbering: stable sort by out-degree descending, then the round-robin deal
-    PBUILD_CUDA(cudaMalloc(&k0, (size_t)V * 4)); PBUILD_CUDA(cudaMalloc(&k1, (size_t)V * 4));
-    PBUILD_CUDA(cudaMalloc(&v0, (size_t)V * 4)); PBUILD_CUDA(cudaMalloc(&v1, (size_t)V * 4));
+    PBUILD_CUDA(vglb_dev_alloc(&k0, (size_t)V * 4)); PBUILD_CUDA(vglb_dev_alloc(&k1, (size_t)V * 4));
+    PBUILD_CUDA(vglb_dev_alloc(&v0, (size_t)V * 4)); PBUILD_CUDA(vglb_dev_alloc(&v1, (size_t)V * 4));
     part_sort_keys_kernel<<<(unsigned)ceil_div64(V, 256), 256, 0, st>>>(d_deg_out, V, k0, v0);
     PBUILD_CUDA(cudaGetLastError());
     const int64_t cols = (int64_t)vp * P;
@@ -552,18 +553,18 @@ static int build_partitioned(vglb_ctx *ctx, vglb_comm *comm, int32_t V, const Ed
         cub::DoubleBuffer<uint32_t> keys(k0, k1), vals(v0, v1);
         size_t tmp_bytes = 0;
         PBUILD_CUDA(cub::DeviceRadixSort::SortPairs(NULL, tmp_bytes, keys, vals, V, 0, 32, st));
-        PBUILD_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+        PBUILD_CUDA(vglb_dev_alloc(&tmp, tmp_bytes ? tmp_bytes : 16));
         PBUILD_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, vals, V, 0, 32, st));
-        PBUILD_CUDA(cudaMalloc(&g->d_fwd, (size_t)V * 4));
-        PBUILD_CUDA(cudaMalloc(&g->d_bwd, (size_t)cols * 4));
+        PBUILD_CUDA(vglb_dev_alloc(&g->d_fwd, (size_t)V * 4));
+        PBUILD_CUDA(vglb_dev_alloc(&g->d_bwd, (size_t)cols * 4));
         PBUILD_CUDA(cudaMemsetAsync(g->d_bwd, 0xFF, (size_t)cols * 4, st));
         part_numbering_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(vals.Current(), V, P, vp, rank, d_deg_out, d_deg_in, g->d_fwd,
                                                                 g->d_bwd, d_misc);
         PBUILD_CUDA(cudaGetLastError());
         PBUILD_CUDA(cudaStreamSynchronize(st));
-        cudaFree(tmp); tmp = NULL;
+        vglb_dev_free(tmp); tmp = NULL;
     }
-    cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1);
+    vglb_dev_free(k0); vglb_dev_free(k1); vglb_dev_free(v0); vglb_dev_free(v1);
     k0 = k1 = v0 = v1 = NULL;
     unsigned long long totals[2] = {0, 0};
     PBUILD_CUDA(cudaMemcpy(totals, d_misc, 16, cudaMemcpyDeviceToHost));
@@ -578,7 +579,7 @@ static int build_partitioned(vglb_ctx *ctx, vglb_comm *comm, int32_t V, const Ed
     g->comm = comm;
 
     // PageRank's inverse in-degrees of the owned rows come from pass 1 (the single-GPU path counts them from the CSR)
-    PBUILD_CUDA(cudaMalloc(&g->d_pr_inv, (size_t)(vp > 0 ? vp : 1) * 4));
+    PBUILD_CUDA(vglb_dev_alloc(&g->d_pr_inv, (size_t)(vp > 0 ? vp : 1) * 4));
     PBUILD_CUDA(cudaMemsetAsync(g->d_pr_inv, 0, (size_t)vp * 4, st));
     if (rows > 0)
     {
@@ -587,7 +588,7 @@ static int build_partitioned(vglb_ctx *ctx, vglb_comm *comm, int32_t V, const Ed
     }
 
     // pass 2, once per direction
-    PBUILD_CUDA(cudaMalloc(&d_rowcnt, ((size_t)vp + 2) * 8));
+    PBUILD_CUDA(vglb_dev_alloc(&d_rowcnt, ((size_t)vp + 2) * 8));
     for (int dir = 0; dir < ((flags & VGLB_GRAPH_WITH_INCOMING) ? 2 : 1); dir++)
     {
         const int64_t e_local = (int64_t)totals[dir];
@@ -598,8 +599,8 @@ static int build_partitioned(vglb_ctx *ctx, vglb_comm *comm, int32_t V, const Ed
             return VGLB_EINVAL;
         }
         const size_t kb = (size_t)(e_local > 0 ? e_local : 1) * 8;
-        PBUILD_CUDA(cudaMalloc(&keys0, kb));
-        PBUILD_CUDA(cudaMalloc(&keys1, kb));
+        PBUILD_CUDA(vglb_dev_alloc(&keys0, kb));
+        PBUILD_CUDA(vglb_dev_alloc(&keys1, kb));
         PBUILD_CUDA(cudaMemsetAsync(d_rowcnt, 0, ((size_t)vp + 2) * 8, st));
         PBUILD_CUDA(cudaMemsetAsync(d_misc + 2, 0, 8, st));
         for (int half = 0; half < halves; half++)
@@ -623,15 +624,15 @@ static int build_partitioned(vglb_ctx *ctx, vglb_comm *comm, int32_t V, const Ed
         }
         int64_t **ptr_field = dir == 0 ? &g->d_out_ptr : &g->d_in_ptr;
         int32_t **adj_field = dir == 0 ? &g->d_out_adj : &g->d_in_adj;
-        PBUILD_CUDA(cudaMalloc(ptr_field, ((size_t)vp + 2) * 8));
-        PBUILD_CUDA(cudaMalloc(adj_field, (size_t)(e_local > 0 ? e_local : 1) * 4 + 16));
+        PBUILD_CUDA(vglb_dev_alloc(ptr_field, ((size_t)vp + 2) * 8));
+        PBUILD_CUDA(vglb_dev_alloc(adj_field, (size_t)(e_local > 0 ? e_local : 1) * 4 + 16));
         {
             size_t tmp_bytes = 0;
             PBUILD_CUDA(cub::DeviceScan::ExclusiveSum(NULL, tmp_bytes, (const int64_t *)d_rowcnt, *ptr_field, vp + 1, st));
-            PBUILD_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+            PBUILD_CUDA(vglb_dev_alloc(&tmp, tmp_bytes ? tmp_bytes : 16));
             PBUILD_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, (const int64_t *)d_rowcnt, *ptr_field, vp + 1, st));
             PBUILD_CUDA(cudaStreamSynchronize(st));
-            cudaFree(tmp); tmp = NULL;
+            vglb_dev_free(tmp); tmp = NULL;
         }
         if (e_local > 0)
         {
@@ -639,14 +640,14 @@ static int build_partitioned(vglb_ctx *ctx, vglb_comm *comm, int32_t V, const Ed
             size_t tmp_bytes = 0;
             const int end_bit = 32 + bits_for64(vp);
             PBUILD_CUDA(cub::DeviceRadixSort::SortKeys(NULL, tmp_bytes, keys, e_local, 0, end_bit, st));
-            PBUILD_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+            PBUILD_CUDA(vglb_dev_alloc(&tmp, tmp_bytes ? tmp_bytes : 16));
             PBUILD_CUDA(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, keys, e_local, 0, end_bit, st));
             part_adjacency_kernel<<<grid, 256, 0, st>>>(keys.Current(), e_local, P, vp, *adj_field);
             PBUILD_CUDA(cudaGetLastError());
             PBUILD_CUDA(cudaStreamSynchronize(st));
-            cudaFree(tmp); tmp = NULL;
+            vglb_dev_free(tmp); tmp = NULL;
         }
-        cudaFree(keys0); cudaFree(keys1);
+        vglb_dev_free(keys0); vglb_dev_free(keys1);
         keys0 = keys1 = NULL;
         if (dir == 0) g->E = e_local;
     }
@@ -729,19 +730,19 @@ extern "C" int vglb_graph_from_csr_partitioned(vglb_ctx *ctx, vglb_comm *comm, i
     g->part_world = P;
     g->col_of_row0 = rank * vp;
     g->comm = comm;
-    PBUILD_CUDA(cudaMalloc(&g->d_out_ptr, ((size_t)vp + 2) * 8));
-    PBUILD_CUDA(cudaMalloc(&g->d_out_adj, (size_t)(E > 0 ? E : 1) * 4 + 16));
+    PBUILD_CUDA(vglb_dev_alloc(&g->d_out_ptr, ((size_t)vp + 2) * 8));
+    PBUILD_CUDA(vglb_dev_alloc(&g->d_out_adj, (size_t)(E > 0 ? E : 1) * 4 + 16));
     PBUILD_CUDA(cudaMemcpyAsync(g->d_out_ptr, h_out_ptr, ((size_t)rows + 1) * 8, cudaMemcpyHostToDevice, st));
     PBUILD_CUDA(cudaMemcpyAsync(g->d_out_adj, h_out_adj, (size_t)E * 4, cudaMemcpyHostToDevice, st));
     if (h_in_ptr)
     {
-        PBUILD_CUDA(cudaMalloc(&g->d_in_ptr, ((size_t)vp + 2) * 8));
-        PBUILD_CUDA(cudaMalloc(&g->d_in_adj, (size_t)(E_in > 0 ? E_in : 1) * 4 + 16));
+        PBUILD_CUDA(vglb_dev_alloc(&g->d_in_ptr, ((size_t)vp + 2) * 8));
+        PBUILD_CUDA(vglb_dev_alloc(&g->d_in_adj, (size_t)(E_in > 0 ? E_in : 1) * 4 + 16));
         PBUILD_CUDA(cudaMemcpyAsync(g->d_in_ptr, h_in_ptr, ((size_t)rows + 1) * 8, cudaMemcpyHostToDevice, st));
         PBUILD_CUDA(cudaMemcpyAsync(g->d_in_adj, h_in_adj, (size_t)E_in * 4, cudaMemcpyHostToDevice, st));
     }
-    PBUILD_CUDA(cudaMalloc(&g->d_fwd, (size_t)V * 4));
-    PBUILD_CUDA(cudaMalloc(&g->d_bwd, (size_t)g->cols * 4));
+    PBUILD_CUDA(vglb_dev_alloc(&g->d_fwd, (size_t)V * 4));
+    PBUILD_CUDA(vglb_dev_alloc(&g->d_bwd, (size_t)g->cols * 4));
     PBUILD_CUDA(cudaMemcpyAsync(g->d_fwd, h_orig_to_col, (size_t)V * 4, cudaMemcpyHostToDevice, st));
     PBUILD_CUDA(cudaMemsetAsync(g->d_bwd, 0xFF, (size_t)g->cols * 4, st));
     part_invert_map_kernel<<<(unsigned)ceil_div64(V, 256), 256, 0, st>>>(g->d_fwd, V, g->d_bwd);

@@ -143,10 +143,10 @@ static int sssp_partitioned_dense(vglb_ctx *ctx, vglb_graph *g, const float *d_w
     CUDA_TRY(cudaSetDevice(ctx->device));
     vglb_comm *comm = g->comm;
     const int32_t rank = g->part_rank, vp = g->vp, rows = g->V, col0 = g->col_of_row0;
-    if (!g->d_part_vec) CUDA_TRY(cudaMalloc(&g->d_part_vec, (size_t)g->cols * 4));
-    if (!g->d_part_prev) CUDA_TRY(cudaMalloc(&g->d_part_prev, (size_t)vp * 4));
-    if (!g->d_queue[0]) CUDA_TRY(cudaMalloc(&g->d_queue[0], ((size_t)vp + 3) * 4));
-    if (!g->d_queue[1]) CUDA_TRY(cudaMalloc(&g->d_queue[1], ((size_t)vp + 3) * 4));
+    if (!g->d_part_vec) CUDA_TRY(vglb_dev_alloc(&g->d_part_vec, (size_t)g->cols * 4));
+    if (!g->d_part_prev) CUDA_TRY(vglb_dev_alloc(&g->d_part_prev, (size_t)vp * 4));
+    if (!g->d_queue[0]) CUDA_TRY(vglb_dev_alloc(&g->d_queue[0], ((size_t)vp + 3) * 4));
+    if (!g->d_queue[1]) CUDA_TRY(vglb_dev_alloc(&g->d_queue[1], ((size_t)vp + 3) * 4));
     const int64_t launches0 = ctx->launches;
     const int32_t b0 = g->tier_border[0], b1 = g->tier_border[1];
     unsigned long long *d_cnt = (unsigned long long *)ctx->d_counters;
@@ -559,17 +559,17 @@ static int sssp_run(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, int32_
     const size_t words_full = (size_t)(g->cols + 31) / 32;  // changed bitmap over all columns
     if (!g->d_queue[0])
     {
-        CUDA_TRY(cudaMalloc(&g->d_queue[0], ((size_t)vp + 3) * 4));
-        CUDA_TRY(cudaMalloc(&g->d_queue[1], ((size_t)vp + 3) * 4));
+        CUDA_TRY(vglb_dev_alloc(&g->d_queue[0], ((size_t)vp + 3) * 4));
+        CUDA_TRY(vglb_dev_alloc(&g->d_queue[1], ((size_t)vp + 3) * 4));
     }
-    if (!g->d_visited) CUDA_TRY(cudaMalloc(&g->d_visited, (words + 32) * 4));
-    if (!g->d_front_bm[0]) CUDA_TRY(cudaMalloc(&g->d_front_bm[0], (words + 32) * 4));
+    if (!g->d_visited) CUDA_TRY(vglb_dev_alloc(&g->d_visited, (words + 32) * 4));
+    if (!g->d_front_bm[0]) CUDA_TRY(vglb_dev_alloc(&g->d_front_bm[0], (words + 32) * 4));
     uint32_t *dist = (uint32_t *)d_dist, *changed_bm = NULL;
     const uint32_t **d_peer_table = NULL;
     if (part)
     {
-        if (!g->d_part_bm[0]) CUDA_TRY(cudaMalloc(&g->d_part_bm[0], (words_full + 32) * 4));
-        if (!g->d_part_stage) CUDA_TRY(cudaMalloc(&g->d_part_stage, (words_full + 32) * 4));
+        if (!g->d_part_bm[0]) CUDA_TRY(vglb_dev_alloc(&g->d_part_bm[0], (words_full + 32) * 4));
+        if (!g->d_part_stage) CUDA_TRY(vglb_dev_alloc(&g->d_part_stage, (words_full + 32) * 4));
         dist = g->d_part_vec;
         changed_bm = g->d_part_bm[0];
         d_peer_table = (const uint32_t **)(ctx->d_counters + 24); // 8 device pointers
@@ -737,7 +737,7 @@ extern "C" int vglb_sssp(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, i
     {
         VGLB_REQUIRE(g->d_bwd != NULL, "vglb_sssp: partitioned graph without a column map");
         CUDA_TRY(cudaSetDevice(ctx->device));
-        if (!g->d_part_vec) CUDA_TRY(cudaMalloc(&g->d_part_vec, (size_t)g->cols * 4));
+        if (!g->d_part_vec) CUDA_TRY(vglb_dev_alloc(&g->d_part_vec, (size_t)g->cols * 4));
         // map the peers' distance replicas once per graph; every rank must end up in the same mode
         if (g->vec_peers_mapped == 0)
         {
