@@ -93,6 +93,17 @@ int vglb_graph_from_csr(vglb_ctx *ctx, int32_t vertices, int64_t edges, const in
                         const int32_t *h_in_adj, vglb_graph **out_graph);
 int vglb_graph_free(vglb_ctx *ctx, vglb_graph *g);
 
+/* ---- the reference's on-disk formats (csrc/graph_io.cu) ----
+ * .el_container: EdgesContainer::save_to_binary_file / load_from_binary_file (graph_generation/edges_container.h:58-99),
+ *                the apps' `-import <file>` input (cmd_parser.hpp:64-68).
+ * .vgl / .vcsr : VGL_Graph::save_to_binary_file / load_from_binary_file (vgl_graph.hpp:109-161) with VECTOR_CSR_GRAPH
+ *                containers (vect_csr_graph.hpp:141-180). Written files are byte-identical to the reference's. */
+int vglb_el_container_save(const char *path, int32_t vertices, int64_t edges, const int32_t *h_src, const int32_t *h_dst);
+int vglb_graph_import_el_container(vglb_ctx *ctx, const char *path, int flags, vglb_graph **out_graph);
+int vglb_graph_save_vgl(vglb_ctx *ctx, const char *path, int32_t vertices, int64_t edges, const int32_t *src,
+                        const int32_t *dst, int src_on_device);
+int vglb_graph_load_vgl(vglb_ctx *ctx, const char *path, int flags, vglb_graph **out_graph);
+
 #define VGLB_NUM_TIERS 8
 typedef struct vglb_graph_info
 {

@@ -200,12 +200,56 @@ def ref_lib(profile: str) -> C.CDLL:
         L.vglref_sssp.restype = C.c_double
         L.vglref_cc.argtypes = [C.c_void_p, _i32p]
         L.vglref_cc.restype = C.c_double
+        if hasattr(L, "vglref_graph_save"):  # file-format entry points (older prebuilt harnesses lack them)
+            L.vglref_edges_save.argtypes = [C.c_char_p, C.c_int, C.c_longlong, _i32p, _i32p]
+            L.vglref_graph_create_from_edges_file.argtypes = [C.c_char_p]
+            L.vglref_graph_create_from_edges_file.restype = C.c_void_p
+            L.vglref_graph_save.argtypes = [C.c_void_p, C.c_char_p]
+            L.vglref_graph_load.argtypes = [C.c_char_p]
+            L.vglref_graph_load.restype = C.c_void_p
+            L.vglref_graph_vertices.argtypes = [C.c_void_p]
+            L.vglref_graph_edges.argtypes = [C.c_void_p]
+            L.vglref_graph_edges.restype = C.c_longlong
         _REF_LIBS[profile] = L
     return _REF_LIBS[profile]
 
 
+def ref_save_edges(path: str, V: int, src: np.ndarray, dst: np.ndarray, profile: str = "bfs"):
+    """EdgesContainer::save_to_binary_file of the unmodified reference."""
+    rc = ref_lib(profile).vglref_edges_save(os.fsencode(path), V, len(src), np.ascontiguousarray(src, np.int32),
+                                            np.ascontiguousarray(dst, np.int32))
+    if rc != 0:
+        raise RuntimeError("EdgesContainer::save_to_binary_file failed")
+
+
 class RefGraph:
     """The reference's own VGL_Graph(VECTOR_CSR_GRAPH) built from an edge list (vgl_graph.hpp:57-68)."""
+
+    @classmethod
+    def _adopt(cls, L, handle):
+        if not handle:
+            raise RuntimeError("the reference could not read the file")
+        self = cls.__new__(cls)
+        self.L, self.h = L, handle
+        self.V, self.E = L.vglref_graph_vertices(handle), L.vglref_graph_edges(handle)
+        return self
+
+    @classmethod
+    def from_edges_file(cls, path: str, profile: str = "bfs"):
+        """EdgesContainer::load_from_binary_file + VGL_Graph::import — the apps' `-import <file>` path."""
+        L = ref_lib(profile)
+        return cls._adopt(L, L.vglref_graph_create_from_edges_file(os.fsencode(path)))
+
+    @classmethod
+    def load(cls, path: str, profile: str = "bfs"):
+        """VGL_Graph::load_from_binary_file."""
+        L = ref_lib(profile)
+        return cls._adopt(L, L.vglref_graph_load(os.fsencode(path)))
+
+    def save(self, path: str):
+        """VGL_Graph::save_to_binary_file."""
+        if self.L.vglref_graph_save(self.h, os.fsencode(path)) != 0:
+            raise RuntimeError("VGL_Graph::save_to_binary_file failed")
 
     def __init__(self, V: int, src: np.ndarray, dst: np.ndarray, profile: str = "pr"):
         self.L = ref_lib(profile)

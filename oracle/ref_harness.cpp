@@ -243,4 +243,84 @@ double vglref_cc(void *h, int *labels_orig)
     catch (const char *e) { fprintf(stderr, "vglref: %s\n", e); return -1; }
 }
 
+/* ---- file formats (pin libvgl_b200's readers / writers against the reference's own) ----
+ * EdgesContainer::save_to_binary_file (vgl_runtime/graph_generation/edges_container.h:58-76) and
+ * VGL_Graph::save_to_binary_file / load_from_binary_file (vgl_graph.hpp:109-161). */
+int vglref_edges_save(const char *path, int vertices, long long edges, const int *src, const int *dst)
+{
+    try
+    {
+        StdoutSilencer quiet;
+        EdgesContainer ec(vertices, edges);
+        memcpy(ec.get_src_ids(), src, sizeof(int) * (size_t)edges);
+        memcpy(ec.get_dst_ids(), dst, sizeof(int) * (size_t)edges);
+        return ec.save_to_binary_file(path) ? 0 : 1;
+    }
+    catch (const char *e) { fprintf(stderr, "vglref: %s\n", e); return 2; }
+}
+
+/* import of an .el_container file, the `-import <file>` path of the apps (cmd_parser.hpp:64-68) */
+void *vglref_graph_create_from_edges_file(const char *path)
+{
+    try
+    {
+        StdoutSilencer quiet;
+        if (!g_inited)
+        {
+            char arg0[] = "vglref";
+            char *argv[] = {arg0, NULL};
+            VGL_RUNTIME::init_library(1, argv);
+            g_inited = true;
+        }
+        EdgesContainer ec;
+        if (!ec.load_from_binary_file(path)) return NULL;
+        RefGraph *rg = new RefGraph;
+        rg->graph = new VGL_Graph(VECTOR_CSR_GRAPH);
+        rg->graph->import(ec);
+        rg->edges = ec.get_edges_count();
+        rg->vertices = ec.get_vertices_count();
+        return rg;
+    }
+    catch (const char *e) { fprintf(stderr, "vglref: %s\n", e); return NULL; }
+    catch (string e) { fprintf(stderr, "vglref: %s\n", e.c_str()); return NULL; }
+}
+
+int vglref_graph_save(void *h, const char *path)
+{
+    RefGraph *rg = (RefGraph *)h;
+    StdoutSilencer quiet;
+    return rg->graph->save_to_binary_file(path) ? 0 : 1;
+}
+
+void *vglref_graph_load(const char *path)
+{
+    try
+    {
+        StdoutSilencer quiet;
+        if (!g_inited)
+        {
+            char arg0[] = "vglref";
+            char *argv[] = {arg0, NULL};
+            VGL_RUNTIME::init_library(1, argv);
+            g_inited = true;
+        }
+        RefGraph *rg = new RefGraph;
+        rg->graph = new VGL_Graph(VECTOR_CSR_GRAPH);
+        if (!rg->graph->load_from_binary_file(path))
+        {
+            delete rg->graph;
+            delete rg;
+            return NULL;
+        }
+        rg->edges = rg->graph->get_edges_count();
+        rg->vertices = rg->graph->get_vertices_count();
+        return rg;
+    }
+    catch (const char *e) { fprintf(stderr, "vglref: %s\n", e); return NULL; }
+    catch (string e) { fprintf(stderr, "vglref: %s\n", e.c_str()); return NULL; }
+}
+
+int vglref_graph_vertices(void *h) { return ((RefGraph *)h)->vertices; }
+long long vglref_graph_edges(void *h) { return ((RefGraph *)h)->edges; }
+
 } // extern "C"

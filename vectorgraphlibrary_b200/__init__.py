@@ -87,6 +87,10 @@ _SIGNATURES = {
     "vglb_graph_from_edges": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, C.c_int, C.c_int, C.POINTER(_P)]),
     "vglb_graph_from_csr": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(_P)]),
     "vglb_graph_free": (C.c_int, [_P, _P]),
+    "vglb_el_container_save": (C.c_int, [C.c_char_p, C.c_int32, C.c_int64, _P, _P]),
+    "vglb_graph_import_el_container": (C.c_int, [_P, C.c_char_p, C.c_int, C.POINTER(_P)]),
+    "vglb_graph_save_vgl": (C.c_int, [_P, C.c_char_p, C.c_int32, C.c_int64, _P, _P, C.c_int]),
+    "vglb_graph_load_vgl": (C.c_int, [_P, C.c_char_p, C.c_int, C.POINTER(_P)]),
     "vglb_graph_get_info": (C.c_int, [_P, C.POINTER(GraphInfo)]),
     "vglb_graph_threshold_vertex": (C.c_int, [_P, _P, C.c_int32, C.POINTER(C.c_int32)]),
     "vglb_varray_reorder_u32": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int]),
@@ -160,6 +164,21 @@ def generate_edges_host(kind: int, scale: int, edge_factor: int, seed: int = MAS
     src, dst = np.empty(E, np.int32), np.empty(E, np.int32)
     _check(lib().vglb_generate_edges_host(kind, scale, E, seed, abc[0], abc[1], abc[2], src.ctypes.data, dst.ctypes.data))
     return src, dst
+
+
+def save_el_container(path: str, V: int, src: np.ndarray, dst: np.ndarray):
+    """EdgesContainer::save_to_binary_file."""
+    src, dst = np.ascontiguousarray(src, np.int32), np.ascontiguousarray(dst, np.int32)
+    _check(lib().vglb_el_container_save(os.fsencode(path), V, len(src), src.ctypes.data, dst.ctypes.data))
+
+
+def save_vgl(ctx: "Context", path: str, V: int, src, dst):
+    """VGL_Graph::import + save_to_binary_file: both VectorCSRGraph containers built on the GPU, reference file format."""
+    on_device = isinstance(src, DeviceArray)
+    E = src.n if on_device else len(src)
+    if not on_device:
+        src, dst = np.ascontiguousarray(src, np.int32), np.ascontiguousarray(dst, np.int32)
+    _check(lib().vglb_graph_save_vgl(ctx.h, os.fsencode(path), V, E, _ptr(src), _ptr(dst), int(on_device)))
 
 
 def pinned_array(n: int, dtype):
@@ -360,6 +379,20 @@ class Graph:
             dst = np.ascontiguousarray(dst, np.int32)
         h = _P()
         _check(lib().vglb_graph_from_edges(ctx.h, V, E, _ptr(src), _ptr(dst), int(on_device), flags, C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def import_el_container(cls, ctx: Context, path: str, flags: int = 0) -> "Graph":
+        """VGL_Graph::import of an .el_container file (the apps' `-import <file>`)."""
+        h = _P()
+        _check(lib().vglb_graph_import_el_container(ctx.h, os.fsencode(path), flags, C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def load_vgl(cls, ctx: Context, path: str, flags: int = 0) -> "Graph":
+        """VGL_Graph::load_from_binary_file + move_to_device."""
+        h = _P()
+        _check(lib().vglb_graph_load_vgl(ctx.h, os.fsencode(path), flags, C.byref(h)))
         return cls(ctx, h)
 
     @classmethod

@@ -454,6 +454,56 @@ extern "C" int vglb_graph_from_csr(vglb_ctx *ctx, int32_t V, int64_t E, const in
     return VGLB_OK;
 }
 
+// incoming CSR of an uploaded graph, derived on the device from the outgoing one (same numbering)
+__global__ void row_of_position_kernel(const int64_t *__restrict__ ptr, int32_t V, uint32_t *__restrict__ row_of_pos)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t v = warp; v < V; v += nwarps)
+        for (int64_t p = ptr[v] + lane; p < ptr[v + 1]; p += 32) row_of_pos[p] = (uint32_t)v;
+}
+
+__global__ void indegree_from_adj_kernel(const int32_t *__restrict__ adj, int64_t E, unsigned long long *__restrict__ indeg)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < E; i += stride) atomicAdd(&indeg[adj[i]], 1ULL);
+}
+
+int vglb_graph_derive_incoming(vglb_ctx *ctx, vglb_graph *g)
+{
+    VGLB_REQUIRE(ctx != NULL && g != NULL && g->comm == NULL, "vglb_graph_derive_incoming: needs an unpartitioned graph");
+    if (g->d_in_ptr) return VGLB_OK;
+    const int32_t V = g->V;
+    const int64_t E = g->E;
+    const size_t eb = (size_t)(E ? E : 1) * 4;
+    uint32_t *d_row_of_pos = NULL;
+    int64_t *d_deg = NULL;
+    void *tmp = NULL;
+    auto cleanup = [&]() { vglb_dev_free(d_row_of_pos); vglb_dev_free(d_deg); vglb_dev_free(tmp); };
+    BUILD_CUDA(vglb_dev_alloc(&d_deg, ((size_t)V + 2) * 8));
+    BUILD_CUDA(cudaMemsetAsync(d_deg, 0, ((size_t)V + 2) * 8, ctx->stream));
+    BUILD_CUDA(vglb_dev_alloc(&g->d_in_ptr, ((size_t)V + 2) * 8));
+    BUILD_CUDA(vglb_dev_alloc(&g->d_in_adj, eb + 16));
+    if (E)
+    {
+        BUILD_CUDA(vglb_dev_alloc(&d_row_of_pos, eb));
+        row_of_position_kernel<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(g->d_out_ptr, V, d_row_of_pos);
+        BUILD_CUDA(cudaGetLastError());
+        indegree_from_adj_kernel<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(g->d_out_adj, E, (unsigned long long *)d_deg);
+        BUILD_CUDA(cudaGetLastError());
+    }
+    size_t tmp_bytes = 0;
+    BUILD_CUDA(cub::DeviceScan::ExclusiveSum(NULL, tmp_bytes, d_deg, g->d_in_ptr, V + 1, ctx->stream));
+    BUILD_CUDA(vglb_dev_alloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+    BUILD_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_deg, g->d_in_ptr, V + 1, ctx->stream));
+    BUILD_CUDA(cudaStreamSynchronize(ctx->stream));
+    BUILD_TRY(build_incoming(ctx, V, E, g->d_out_adj, d_row_of_pos, g->d_in_adj));
+    cleanup();
+    return VGLB_OK;
+}
+
 extern "C" int vglb_graph_get_info(vglb_graph *g, vglb_graph_info *info)
 {
     VGLB_REQUIRE(g != NULL && info != NULL, "vglb_graph_get_info: NULL argument");
