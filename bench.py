@@ -262,10 +262,15 @@ def ours(args):
         e2e["seconds"] = comm.max_float(e2e["seconds"])
     e2e_value = edges_per_step / e2e["seconds"] / 1e9
 
+    base_scale = WORKLOADS[args.workload][1]
+    workload_name = desc if not args.scale else desc.replace(f"scale-{base_scale}", f"scale-{scale}")
+    if world > 1:  # weak scaling: the graph grows with the GPU count, per-GPU work is the single-GPU workload
+        workload_name = (workload_name.replace(f"scale-{scale}", f"scale-{runner.scale}")
+                         + f" (weak scaling: scale-{scale} per GPU x {world} GPUs)")
     line = None
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is reported at N = 1 only
             try:
                 _, cpu = cpu_reference_run(args.workload, args.cpu_scale, 2, 1)
             except Exception as ex:  # the checker must not take the product's number down with it
@@ -274,7 +279,7 @@ def ours(args):
             "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if world > 1 and runner.weak else "strong" if world > 1 else "weak",
             "vs_baseline": None, "dtype": runner.dtype, "data": "synthetic",
-            "config": {"workload": desc if not args.scale else desc.replace(f"scale-{WORKLOADS[args.workload][1]}", f"scale-{scale}"),
+            "config": {"workload": workload_name,
                        "vertices": runner.V_total, "edges": runner.E_total, "iterations_per_step": runner.iters_per_step,
                        "partition": runner.partition, "l2": "inputs larger than L2 (adjacency %.2f GB per GPU, L2 126 MB)" % (runner.adj_bytes_per_gpu / 1e9),
                        "seed": hex(vgl.MASTER_SEED)},
