@@ -20,6 +20,7 @@ try:
 except Exception as e: print('no json', e)
 "
 done
+[ -n "${SKIP_NCCL:-}" ] && exit 0
 VGLB_PR_EXCHANGE=nccl $TR --master-port 29640 bench.py --gpus $N --workload pr --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_pr_nccl_n$N.json 2> gpurun_out/bench_pr_nccl_n$N.err; echo "bench pr nccl rc=$?"
 python -c "
 import json

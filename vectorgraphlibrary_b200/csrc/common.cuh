@@ -108,7 +108,8 @@ struct vglb_graph
     // PageRank peer-store exchange: the peers' copies of the two contribution vectors (CUDA IPC mappings)
     int pr_exchange;            // VGLB_EXCHANGE_NCCL | VGLB_EXCHANGE_P2P
     float *d_pr_peer[2][8];     // [buffer][peer rank]; NULL for this rank
-    uint32_t *d_vec_peer[8];    // the peers' d_part_vec (SSSP distance replicas), CUDA IPC mappings; NULL for this rank
+    void *d_part_lists;         // SSSP: per-owner lists of (column, distance) updates this rank produced in a round
+    uint32_t *d_vec_peer[8];    // the peers' d_part_lists, CUDA IPC mappings (own entry = own buffer)
     int vec_peers_mapped;       // 0 = not tried, 1 = mapped, -1 = mapping failed (dense allreduce exchange is used)
     // BFS / SSSP / CC scratch
     uint32_t *d_visited, *d_front_bm[2];

@@ -189,7 +189,7 @@ int vglb_graph_compute_tiers(vglb_ctx *ctx, vglb_graph *g)
 void vglb_graph_free_fields(vglb_graph *g)
 {
     vglb_dev_free(g->d_part_bm[0]); vglb_dev_free(g->d_part_bm[1]); vglb_dev_free(g->d_part_bm[2]); vglb_dev_free(g->d_part_stage);
-    vglb_dev_free(g->d_part_vec); vglb_dev_free(g->d_part_prev);
+    vglb_dev_free(g->d_part_vec); vglb_dev_free(g->d_part_prev); vglb_dev_free(g->d_part_lists);
     for (int b = 0; b < 2; b++)
         for (int p = 0; p < 8; p++)
             if (g->d_pr_peer[b][p]) cudaIpcCloseMemHandle(g->d_pr_peer[b][p]);

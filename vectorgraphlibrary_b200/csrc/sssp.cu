@@ -20,6 +20,7 @@
 //     (ld.global.nc.L1::no_allocate + L2 evict-first), the distance vector is the L2-resident gather target.
 // HBM roofline: algorithmic bytes = sum_rounds [ 12 e_i (index + weight + dist[dst]) + 24 f_i + 8 n(F_{i+1}) ] + scans.
 #include <float.h>
+#include <time.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -477,45 +478,87 @@ __global__ void sssp_weight_sample_kernel(const float *__restrict__ w, int64_t E
     if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
 }
 
-// owner side of the sparse exchange of a partitioned round: stage holds, for every peer, the slice of its changed bitmap
-// that covers THIS rank's vertices. For every flagged vertex the owner reads the peer's value straight out of the peer's
-// distance replica (CUDA IPC peer memory over NVLink: 4 bytes per update instead of an allreduce of the whole vector),
-// keeps the minimum and marks the vertex due. One thread per 32-vertex word: no atomics.
+// ---- sparse exchange of a partitioned round ---------------------------------------------------------------------------
+// Sender side: the changed bitmap (one bit per column a relaxation of this round lowered in THIS rank's replica) is
+// compacted, per owning rank q, into a contiguous list of (column << 32 | distance bits) entries; lists[q] counts them,
+// the entries of owner q start at lists[P + q * vp]. The bits are cleared on the way. One thread per 32-column word;
+// queue slots are claimed once per warp and owner (__match_any_sync groups the lanes by owner).
 __global__ void __launch_bounds__(256)
-sssp_pull_kernel(const uint32_t *__restrict__ stage, int32_t P, int32_t rank, int32_t wslice, int32_t col0, uint32_t *__restrict__ dist,
-                 const uint32_t *const *__restrict__ peer_dist, uint32_t *__restrict__ near_bm, uint32_t *__restrict__ far_bm,
-                 uint32_t threshold_bits, unsigned long long *counters)
+sssp_compact_updates_kernel(uint32_t *__restrict__ changed_bm, const uint32_t *__restrict__ dist, int32_t words_full, int32_t wslice,
+                            int32_t rank, int32_t P, int32_t vp, unsigned long long *__restrict__ lists)
 {
+    const int lane = threadIdx.x & 31;
     const int32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    long long pulled = 0;
-    if (w < wslice)
+    uint32_t bits = 0;
+    int32_t q = -1;
+    if (w < words_full)
     {
-        uint32_t near_add = 0, far_add = 0;
-        for (int p = 0; p < P; p++)
+        q = w / wslice;
+        if (q != rank) bits = changed_bm[w];
+        if (bits) changed_bm[w] = 0;
+    }
+    const unsigned active = __ballot_sync(0xffffffffu, bits != 0);
+    if (!bits) return;
+    const unsigned peers = __match_any_sync(active, q); // lanes of this warp with updates for the same owner
+    const int cnt = __popc(bits);
+    // exclusive prefix of cnt over the lanes of `peers` below this lane, and the group total
+    int before = 0, total = 0;
+    for (unsigned m = peers; m;)
+    {
+        const int l = __ffs(m) - 1;
+        m &= m - 1;
+        const int c = __shfl_sync(peers, cnt, l);
+        if (l < lane) before += c;
+        total += c;
+    }
+    const int leader = __ffs(peers) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(&lists[q], (unsigned long long)total);
+    base = __shfl_sync(peers, base, leader);
+    unsigned long long *out = lists + P + (int64_t)q * vp + base + before;
+    while (bits)
+    {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const uint32_t col = (uint32_t)(w << 5) + b;
+        *out++ = ((unsigned long long)col << 32) | dist[col];
+    }
+}
+
+// Owner side: read every peer's list for this rank out of the peer's memory (CUDA IPC peer loads over NVLink —
+// contiguous 8-byte entries in full-width transactions; reading the flagged values one by one out of the peers'
+// replicas ran at 6-8 G values/s, NVLink small-read bound), lower the owned distances and mark the improved vertices due.
+__global__ void __launch_bounds__(256)
+sssp_apply_updates_kernel(const unsigned long long *const *__restrict__ peer_lists, int32_t P, int32_t rank, int32_t vp, int32_t col0,
+                          uint32_t *__restrict__ dist, uint32_t *__restrict__ near_bm, uint32_t *__restrict__ far_bm,
+                          uint32_t threshold_bits, unsigned long long *counters)
+{
+    long long applied = 0;
+    for (int p = 0; p < P; p++)
+    {
+        if (p == rank) continue;
+        const unsigned long long *lists = peer_lists[p];
+        const long long n = (long long)lists[rank];
+        const unsigned long long *entries = lists + P + (int64_t)rank * vp;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         {
-            if (p == rank) continue;
-            uint32_t bits = stage[(int64_t)p * wslice + w];
-            const uint32_t *remote = peer_dist[p];
-            while (bits)
+            const unsigned long long e = entries[i];
+            const uint32_t col = (uint32_t)(e >> 32), val = (uint32_t)e;
+            applied++;
+            if (val < dist[col])
             {
-                const int b = __ffs(bits) - 1;
-                bits &= bits - 1;
-                const int32_t col = col0 + (w << 5) + b;
-                const uint32_t val = remote[col];
-                pulled++;
-                if (val < dist[col])
+                const uint32_t old = atomicMin(&dist[col], val);
+                if (val < old)
                 {
-                    dist[col] = val;
-                    if (val < threshold_bits) near_add |= 1u << b;
-                    else far_add |= 1u << b;
+                    const uint32_t r = col - (uint32_t)col0;
+                    uint32_t *bm = val < threshold_bits ? near_bm : far_bm;
+                    atomicOr(&bm[r >> 5], 1u << (r & 31));
                 }
             }
         }
-        if (near_add) near_bm[w] |= near_add;
-        if (far_add) far_bm[w] |= far_add & ~near_add;
     }
-    pulled = warp_sum_i64(pulled);
-    if ((threadIdx.x & 31) == 0 && pulled) atomicAdd(&counters[C_ROWS], (unsigned long long)pulled);
+    applied = warp_sum_i64(applied);
+    if ((threadIdx.x & 31) == 0 && applied) atomicAdd(&counters[C_ROWS], (unsigned long long)applied);
 }
 
 __global__ void sssp_part_seed_kernel(uint32_t *__restrict__ dist, int64_t cols, int32_t source_col, uint32_t *near_bm, int32_t src_row)
@@ -565,14 +608,14 @@ static int sssp_run(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, int32_
     if (!g->d_visited) CUDA_TRY(vglb_dev_alloc(&g->d_visited, (words + 32) * 4));
     if (!g->d_front_bm[0]) CUDA_TRY(vglb_dev_alloc(&g->d_front_bm[0], (words + 32) * 4));
     uint32_t *dist = (uint32_t *)d_dist, *changed_bm = NULL;
-    const uint32_t **d_peer_table = NULL;
+    const unsigned long long **d_peer_table = NULL;
+    unsigned long long *lists = (unsigned long long *)g->d_part_lists;
     if (part)
     {
         if (!g->d_part_bm[0]) CUDA_TRY(vglb_dev_alloc(&g->d_part_bm[0], (words_full + 32) * 4));
-        if (!g->d_part_stage) CUDA_TRY(vglb_dev_alloc(&g->d_part_stage, (words_full + 32) * 4));
         dist = g->d_part_vec;
         changed_bm = g->d_part_bm[0];
-        d_peer_table = (const uint32_t **)(ctx->d_counters + 24); // 8 device pointers
+        d_peer_table = (const unsigned long long **)(ctx->d_counters + 24); // 8 device pointers
         CUDA_TRY(cudaMemcpyAsync(d_peer_table, g->d_vec_peer, sizeof(g->d_vec_peer), cudaMemcpyHostToDevice, ctx->stream));
     }
     const int64_t launches0 = ctx->launches;
@@ -616,6 +659,7 @@ static int sssp_run(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, int32_
         delta = (float)(scale * (double)wmax / (avg_deg > 1.0 ? avg_deg : 1.0));
     }
     const bool trace = getenv("VGLB_SSSP_TRACE") != NULL; // developer aid: one line per selection on stderr
+    double trace_t = 0.0;
     const float inf = FLT_MAX - 100.0f;
     const bool split = delta > 0.f && delta < inf;
     float threshold = split ? delta : inf;
@@ -649,8 +693,6 @@ static int sssp_run(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, int32_
             ctx->launches++;
             rc = vglb_comm_allreduce_async(comm, d_cnt + C_COUNT, C_COUNT, VGLB_DT_I64, VGLB_OP_SUM);
             if (rc != VGLB_OK) return rc;
-            rc = vglb_comm_allreduce_async(comm, d_cnt + 2 * C_COUNT, 1, VGLB_DT_I64, VGLB_OP_MAX);
-            if (rc != VGLB_OK) return rc;
         }
         CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, (2 * C_COUNT + 1) * 8, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
@@ -661,8 +703,16 @@ static int sssp_run(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, int32_
         const long long n_cur = (long long)(gl[C_NEXT_BIG] + gl[C_NEXT_MID] + gl[C_NEXT_SMALL]), pending = (long long)gl[C_FOUND];
         tot_edges += (int64_t)h_cnt[C_EDGES]; // relaxed by the previous round (this rank)
         tot_pulled += (int64_t)h_cnt[C_ROWS];
-        if (trace) fprintf(stderr, "sssp select %lld (%s): threshold %.3f queued %lld (local %lld) pending %lld, previous round relaxed %lld edges\n",
-                           (long long)selects, from_far ? "far" : "near", threshold, n_cur, n_local, pending, (long long)h_cnt[C_EDGES]);
+        if (trace)
+        {
+            struct timespec ts;
+            clock_gettime(CLOCK_MONOTONIC, &ts);
+            const double now = (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+            fprintf(stderr, "sssp select %lld (%s): threshold %.3f queued %lld (local %lld) pending %lld, previous round relaxed %lld edges, pulled %lld, %.1f us since the previous line\n",
+                    (long long)selects, from_far ? "far" : "near", threshold, n_cur, n_local, pending, (long long)h_cnt[C_EDGES],
+                    (long long)h_cnt[C_ROWS], trace_t > 0.0 ? (now - trace_t) * 1e6 : 0.0);
+            trace_t = now;
+        }
         if (n_cur == 0)
         {
             if (!from_far)
@@ -673,6 +723,17 @@ static int sssp_run(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, int32_
                 continue;
             }
             if (pending == 0) break;
+            if (part)
+            {
+                // the smallest pending distance of the whole job (every rank takes this branch: same allreduced counters)
+                unsigned long long *d_min = d_cnt + 2 * C_COUNT;
+                CUDA_TRY(cudaMemcpyAsync(d_min, h_cnt + 2 * C_COUNT, 8, cudaMemcpyHostToDevice, st));
+                rc = vglb_comm_allreduce_async(comm, d_min, 1, VGLB_DT_I64, VGLB_OP_MAX);
+                if (rc != VGLB_OK) return rc;
+                CUDA_TRY(cudaMemcpyAsync(h_cnt + 2 * C_COUNT, d_min, 8, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+                CUDA_TRY(cudaMemsetAsync(d_min, 0, 8, st));
+            }
             const uint32_t min_bits = 0xffffffffu - (uint32_t)(part ? h_cnt[2 * C_COUNT] : h_cnt[C_MF]);
             float min_pending;
             memcpy(&min_pending, &min_bits, 4);
@@ -694,12 +755,17 @@ static int sssp_run(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, int32_
         }
         if (part)
         {
-            rc = vglb_comm_alltoall_async(comm, changed_bm, g->d_part_stage, (size_t)wslice * 4);
-            if (rc != VGLB_OK) return rc;
-            sssp_pull_kernel<<<select_grid, 256, 0, st>>>(g->d_part_stage, P, rank, wslice, col0, dist, d_peer_table, near_bm, far_bm, tbits, d_cnt);
+            CUDA_TRY(cudaMemsetAsync(lists, 0, (size_t)P * 8, st)); // list lengths (the peers finished reading: see below)
+            sssp_compact_updates_kernel<<<(unsigned)ceil_div64((int64_t)words_full, 256), 256, 0, st>>>(changed_bm, dist, (int32_t)words_full, wslice,
+                                                                                                       rank, P, vp, lists);
             KERNEL_TRY();
-            CUDA_TRY(cudaMemsetAsync(changed_bm, 0, words_full * 4, st));
-            ctx->launches++;
+            // barrier: every rank's lists are complete before anybody reads them; the NEXT round's lists are not touched
+            // before every rank has passed the next counter allreduce, i.e. finished reading these
+            rc = vglb_comm_allreduce_async(comm, d_cnt + 2 * C_COUNT + 2, 1, VGLB_DT_I64, VGLB_OP_SUM);
+            if (rc != VGLB_OK) return rc;
+            sssp_apply_updates_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_peer_table, P, rank, vp, col0, dist, near_bm, far_bm, tbits, d_cnt);
+            KERNEL_TRY();
+            ctx->launches += 2;
         }
         rounds++;
         tot_rows += n_local;
@@ -717,10 +783,10 @@ static int sssp_run(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, int32_
         stats->iterations = rounds;
         stats->edges_inspected = tot_edges;
         stats->vertices_processed = tot_rows;
-        // queues, bitmap scans, far-pile distance reads; partitioned: + changed-bitmap slices sent / received / cleared
-        // and 32-byte sectors pulled from the peers
+        // queues, bitmap scans, far-pile distance reads; partitioned: + the changed-bitmap scan of every round and, per
+        // update received, 8 bytes written by the sender + 8 read over NVLink + the owner's 12-byte read-modify-write
         stats->frontier_bytes = 8 * tot_next + selects * (int64_t)words * 4 + far_selects * 4 * (int64_t)rows
-                                + (part ? rounds * (int64_t)words_full * 4 * 3 + 32 * tot_pulled : 0);
+                                + (part ? rounds * (int64_t)words_full * 4 + 28 * tot_pulled : 0);
         stats->algorithmic_bytes = 12 * tot_edges + 24 * tot_rows + stats->frontier_bytes;
         stats->kernel_launches = ctx->launches - launches0;
     }
@@ -738,12 +804,14 @@ extern "C" int vglb_sssp(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, i
         VGLB_REQUIRE(g->d_bwd != NULL, "vglb_sssp: partitioned graph without a column map");
         CUDA_TRY(cudaSetDevice(ctx->device));
         if (!g->d_part_vec) CUDA_TRY(vglb_dev_alloc(&g->d_part_vec, (size_t)g->cols * 4));
-        // map the peers' distance replicas once per graph; every rank must end up in the same mode
+        // the per-owner update lists of this rank: P counters + vp entries per owner; mapped into the peers once per graph
+        // (every rank must end up in the same mode)
+        if (!g->d_part_lists) CUDA_TRY(vglb_dev_alloc(&g->d_part_lists, ((size_t)g->cols + g->part_world + 8) * 8));
         if (g->vec_peers_mapped == 0)
         {
             int ok = 1;
             if (g->part_world > 8 || getenv("VGLB_SSSP_DENSE_EXCHANGE")) ok = 0;
-            else if (vglb_comm_ipc_map(g->comm, g->d_part_vec, (void **)g->d_vec_peer) != VGLB_OK) ok = 0;
+            else if (vglb_comm_ipc_map(g->comm, g->d_part_lists, (void **)g->d_vec_peer) != VGLB_OK) ok = 0;
             int *d_ok = (int *)(ctx->d_counters + 62);
             CUDA_TRY(cudaMemcpyAsync(d_ok, &ok, 4, cudaMemcpyHostToDevice, ctx->stream));
             int rc = vglb_comm_allreduce_async(g->comm, d_ok, 1, VGLB_DT_I32, VGLB_OP_MIN);
