@@ -75,10 +75,43 @@ __device__ __forceinline__ void enqueue_binned_multi(const bool (&won)[BFS_TD_UN
     }
 }
 
-template <int NT, bool PART>
+// how a partitioned top-down level hands a discovery to the vertex's owner
+struct PartArgs
+{
+    int32_t col0, vp, P, rank;
+    unsigned long long *lists; // P counters, then vp 4-byte entries per owner starting at byte offset 8 * P
+};
+
+__device__ __forceinline__ uint32_t *part_list_entries(const PartArgs &A, int q)
+{
+    return reinterpret_cast<uint32_t *>(A.lists + A.P) + (int64_t)q * A.vp;
+}
+
+// append the columns this warp discovered for other ranks to the lists of their owners: one slot claim per owner and warp
+__device__ __forceinline__ void append_remote(const PartArgs &A, bool remote, int32_t v)
+{
+    const unsigned active = __ballot_sync(0xffffffffu, remote);
+    if (!remote) return;
+    const int lane = threadIdx.x & 31;
+    const int q = v / A.vp;
+    const unsigned same = __match_any_sync(active, q);
+    const int leader = __ffs(same) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(&A.lists[q], (unsigned long long)__popc(same));
+    base = __shfl_sync(same, base, leader);
+    part_list_entries(A, q)[base + __popc(same & ((1u << lane) - 1u))] = (uint32_t)v;
+}
+
+// NT threads (a CTA, a warp or an 8-lane group) expand the out-row [s,e) of one frontier vertex.
+// Every thread of the warp must call this together (ballots inside); `e <= s` for idle groups.
+// MODE 0: one GPU. MODE 1: one rank's part, discoveries marked in a candidate bitmap (`levels` reinterpreted) that the
+// owners resolve after an all-to-all. MODE 2: one rank's part, `visited` is this rank's replica: the first thread to set
+// a bit either owns the vertex (level written, queued by local row) or appends the column to its owner's list.
+template <int NT, int MODE>
 __device__ __forceinline__ void td_expand(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, int64_t s, int64_t e, int tid,
                                           uint32_t *__restrict__ visited, int32_t *__restrict__ levels, int32_t next_level,
-                                          int32_t b0, int32_t b1, const TierQueues &nq, unsigned long long *counters, long long &mf)
+                                          int32_t b0, int32_t b1, const TierQueues &nq, unsigned long long *counters, long long &mf,
+                                          const PartArgs &A)
 {
     for (int64_t p0 = s + tid;; p0 += NT * BFS_TD_UNROLL)
     {
@@ -101,7 +134,7 @@ __device__ __forceinline__ void td_expand(const int64_t *__restrict__ ptr, const
             if (v[k] < 0) continue;
             const uint32_t bit = 1u << (v[k] & 31);
             if (seen[k] & bit) continue;
-            if (PART)
+            if (MODE == 1)
             {
                 uint32_t *cand = reinterpret_cast<uint32_t *>(levels);
                 if (!(cand[v[k] >> 5] & bit)) atomicOr(&cand[v[k] >> 5], bit);
@@ -112,7 +145,7 @@ __device__ __forceinline__ void td_expand(const int64_t *__restrict__ ptr, const
                 won[k] = !(old & bit);
             }
         }
-        if (!PART)
+        if (MODE == 0)
         {
 #pragma unroll
             for (int k = 0; k < BFS_TD_UNROLL; k++)
@@ -123,15 +156,33 @@ __device__ __forceinline__ void td_expand(const int64_t *__restrict__ ptr, const
                 }
             enqueue_binned_multi(won, v, b0, b1, nq, counters);
         }
+        if (MODE == 2)
+        {
+            bool mine[BFS_TD_UNROLL];
+            int32_t row[BFS_TD_UNROLL];
+#pragma unroll
+            for (int k = 0; k < BFS_TD_UNROLL; k++)
+            {
+                row[k] = v[k] - A.col0;
+                mine[k] = won[k] && (uint32_t)row[k] < (uint32_t)A.vp;
+                if (mine[k])
+                {
+                    levels[row[k]] = next_level;
+                    mf += ptr[row[k] + 1] - ptr[row[k]];
+                }
+                if (__any_sync(0xffffffffu, won[k] && !mine[k])) append_remote(A, won[k] && !mine[k], v[k]);
+            }
+            enqueue_binned_multi(mine, row, b0, b1, nq, counters);
+        }
     }
 }
 
-template <bool PART>
+template <int MODE>
 __global__ void __launch_bounds__(BFS_THREADS)
 bfs_td_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, TierQueues cq, int32_t n_big, int32_t big_chunks,
               int32_t n_mid, int32_t n_small, int32_t blocks_mid, int32_t blocks_small, uint32_t *__restrict__ visited,
               int32_t *__restrict__ levels, int32_t next_level, int32_t b0, int32_t b1, TierQueues nq,
-              unsigned long long *counters)
+              unsigned long long *counters, PartArgs A)
 {
     const int b = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -143,7 +194,7 @@ bfs_td_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, 
         const int32_t u = cq.q[0][b / big_chunks];
         const int64_t s = ptr[u] + (int64_t)(b % big_chunks) * BFS_BIG_CHUNK, e = min(ptr[u + 1], s + BFS_BIG_CHUNK);
         if (threadIdx.x == 0) edges = max(e - s, (int64_t)0);
-        td_expand<BFS_THREADS, PART>(ptr, adj, s, e, threadIdx.x, visited, levels, next_level, b0, b1, nq, counters, mf);
+        td_expand<BFS_THREADS, MODE>(ptr, adj, s, e, threadIdx.x, visited, levels, next_level, b0, b1, nq, counters, mf, A);
     }
     else if (b < big_blocks + blocks_mid)
     {
@@ -153,7 +204,7 @@ bfs_td_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, 
             const int32_t u = cq.q[1][i];
             const int64_t s = ptr[u], e = ptr[u + 1];
             if (lane == 0) edges += e - s;
-            td_expand<32, PART>(ptr, adj, s, e, lane, visited, levels, next_level, b0, b1, nq, counters, mf);
+            td_expand<32, MODE>(ptr, adj, s, e, lane, visited, levels, next_level, b0, b1, nq, counters, mf, A);
         }
     }
     else
@@ -175,13 +226,51 @@ bfs_td_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, 
                 e = ptr[u + 1];
                 if (gl == 0) edges += e - s;
             }
-            td_expand<G, PART>(ptr, adj, s, e, gl, visited, levels, next_level, b0, b1, nq, counters, mf);
+            td_expand<G, MODE>(ptr, adj, s, e, gl, visited, levels, next_level, b0, b1, nq, counters, mf, A);
         }
     }
     edges = warp_sum_i64(edges);
     mf = warp_sum_i64(mf);
     if (lane == 0 && edges) atomicAdd(&counters[C_EDGES], (unsigned long long)edges);
     if (lane == 0 && mf) atomicAdd(&counters[C_MF], (unsigned long long)mf);
+}
+
+// owner side of a partitioned top-down level: the peers' lists of columns they discovered in this rank's slice, read out
+// of the peers' memory (CUDA IPC). The first claim of a vertex in the owner's visited slice makes the discovery real.
+__global__ void __launch_bounds__(256)
+bfs_apply_lists_kernel(const unsigned long long *const *__restrict__ peer_lists, PartArgs A, const int64_t *__restrict__ ptr,
+                       uint32_t *__restrict__ visited, int32_t *__restrict__ levels_local, int32_t next_level, int32_t b0, int32_t b1,
+                       TierQueues nq, unsigned long long *counters)
+{
+    long long mf = 0;
+    for (int p = 0; p < A.P; p++)
+    {
+        if (p == A.rank) continue;
+        const unsigned long long *lists = peer_lists[p];
+        const long long n = (long long)lists[A.rank];
+        const uint32_t *entries = reinterpret_cast<const uint32_t *>(lists + A.P) + (int64_t)A.rank * A.vp;
+        const long long n_padded = (n + 31) & ~31LL;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_padded; i += (long long)gridDim.x * blockDim.x)
+        {
+            bool won = false;
+            int32_t row = 0;
+            if (i < n)
+            {
+                const uint32_t v = entries[i];
+                const uint32_t bit = 1u << (v & 31);
+                if (!(visited[v >> 5] & bit)) won = !(atomicOr(&visited[v >> 5], bit) & bit);
+                row = (int32_t)v - A.col0;
+                if (won)
+                {
+                    levels_local[row] = next_level;
+                    mf += ptr[row + 1] - ptr[row];
+                }
+            }
+            enqueue_binned(won, row, b0, b1, nq, counters);
+        }
+    }
+    mf = warp_sum_i64(mf);
+    if ((threadIdx.x & 31) == 0 && mf) atomicAdd(&counters[C_MF], (unsigned long long)mf);
 }
 
 // bottom-up step. A warp takes 32 consecutive words of the visited bitmap per pass: lane l loads word l (one coalesced
@@ -497,8 +586,8 @@ __global__ void bfs_copy_counters_kernel(unsigned long long *c)
     if (threadIdx.x < C_COUNT) c[C_COUNT + threadIdx.x] = c[threadIdx.x];
 }
 
-static int bfs_partitioned(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t *d_levels, const vglb_bfs_opts *opts,
-                           vglb_stats *stats)
+static int bfs_partitioned_bitmaps(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t *d_levels, const vglb_bfs_opts *opts,
+                                   vglb_stats *stats)
 {
     VGLB_REQUIRE(source >= 0 && source < g->cols, "vglb_bfs: source column out of range");
     const bool dopt = opts && opts->direction_optimising;
@@ -557,6 +646,13 @@ static int bfs_partitioned(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t
     const int max_blocks = ctx->sm_count * 16;
     const int big_chunks = (int)ceil_div64(g->max_degree > 0 ? g->max_degree : 1, BFS_BIG_CHUNK);
     int rc;
+    const bool trace = getenv("VGLB_BFS_TRACE") != NULL;
+    double trace_t = 0.0;
+    if (trace)
+    {
+        cudaStreamSynchronize(st);
+        trace_t = trace_now();
+    }
 
     while (n_cur > 0)
     {
@@ -568,9 +664,9 @@ static int bfs_partitioned(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t
             const int64_t grid = (int64_t)n[0] * big_chunks + blocks_mid + blocks_small;
             if (grid > 0)
             {
-                bfs_td_kernel<true><<<(unsigned)grid, BFS_THREADS, 0, st>>>(g->d_out_ptr, g->d_out_adj, cq, n[0], big_chunks, n[1], n[2], blocks_mid,
-                                                                          blocks_small, visited, (int32_t *)next_bm, level + 1, b0, b1,
-                                                                          cq, d_cnt);
+                bfs_td_kernel<1><<<(unsigned)grid, BFS_THREADS, 0, st>>>(g->d_out_ptr, g->d_out_adj, cq, n[0], big_chunks, n[1], n[2], blocks_mid,
+                                                                       blocks_small, visited, (int32_t *)next_bm, level + 1, b0, b1,
+                                                                       cq, d_cnt, PartArgs());
                 KERNEL_TRY();
                 ctx->launches++;
             }
@@ -607,6 +703,13 @@ static int bfs_partitioned(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t
         levels_run++;
         const unsigned long long *gl = h_cnt + C_COUNT; // global sums
         const long long n_next = (long long)gl[C_FOUND];
+        if (trace)
+        {
+            const double now = trace_now();
+            fprintf(stderr, "bfs level %d (%s, rank %d of %d): frontier %lld, this rank inspected %lld edges, found %lld, %.1f us since the previous line\n",
+                    level, bottom_up ? "bottom-up" : "top-down", rank, P, n_cur, (long long)h_cnt[C_EDGES], n_next, (now - trace_t) * 1e6);
+            trace_t = now;
+        }
         tot_edges += (int64_t)h_cnt[C_EDGES];
         tot_rows += bottom_up ? (int64_t)h_cnt[C_ROWS] : (int64_t)n[0] + n[1] + n[2];
         tot_frontier_bytes += words * 4 * 3; // allgathered frontier written, ORed into visited
@@ -668,6 +771,228 @@ static int bfs_partitioned(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t
     return VGLB_OK;
 }
 
+// ---- 1D-partitioned BFS, discovery lists (the default; bfs_partitioned_bitmaps above is the fallback without CUDA IPC) ----
+// A top-down level with a small frontier should not cost full-length bitmap traffic (memset + all-to-all + allgather + OR of
+// V/8-byte bitmaps cost ~150 us per level at 2 GPUs and grow with V). Here every rank keeps its own replica of the visited
+// bitmap: the first thread to set a bit either owns the vertex — level written, queued by local row — or appends the
+// column to the list of its owner (at most once per rank and vertex in a whole run, so a list never outgrows the owner's
+// slice). After a one-word allreduce as barrier every owner reads the lists addressed to it out of the peers' memory
+// (bfs_apply_lists_kernel) and claims the vertices in its own slice, which is authoritative. Replicas may lag behind —
+// a stale bit only costs a duplicate list entry. Bottom-up levels work as before on the owned slice and allgather the new
+// frontier slices; at a top-down -> bottom-up switch the frontier bitmap is assembled once from the owners' queues.
+static int bfs_partitioned(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t *d_levels, const vglb_bfs_opts *opts,
+                           vglb_stats *stats)
+{
+    VGLB_REQUIRE(source >= 0 && source < g->cols, "vglb_bfs: source column out of range");
+    const bool dopt = opts && opts->direction_optimising;
+    if (dopt && !g->d_in_ptr)
+    {
+        vglb_set_error("vglb_bfs: direction-optimising BFS needs a graph built with VGLB_GRAPH_WITH_INCOMING");
+        return VGLB_EINVAL;
+    }
+    const long long alpha = (opts && opts->alpha > 0) ? opts->alpha : 15;
+    const long long beta = (opts && opts->beta > 0) ? opts->beta : 18;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    vglb_comm *comm = g->comm;
+    const int32_t P = g->part_world, rank = g->part_rank, vp = g->vp, rows = g->V;
+    const int32_t wslice = vp / 32;
+    const int64_t words = g->cols / 32, my = (int64_t)rank * wslice;
+    for (int i = 0; i < 3; i++)
+        if (!g->d_part_bm[i]) CUDA_TRY(vglb_dev_alloc(&g->d_part_bm[i], (size_t)(words + 32) * 4));
+    for (int i = 0; i < 2; i++)
+        if (!g->d_queue[i]) CUDA_TRY(vglb_dev_alloc(&g->d_queue[i], ((size_t)vp + 3) * 4));
+    int rc = bfs_prepare_no_in_edges(ctx, g);
+    if (rc != VGLB_OK) return rc;
+    const int64_t launches0 = ctx->launches;
+    const int32_t b0 = g->tier_border[0], b1 = g->tier_border[1];
+    unsigned long long *d_cnt = (unsigned long long *)ctx->d_counters;
+    unsigned long long *h_cnt = (unsigned long long *)ctx->h_counters;
+    cudaStream_t st = ctx->stream;
+    auto regions = [&](int32_t *base) {
+        TierQueues q;
+        q.q[0] = base;
+        q.q[1] = base + b0;
+        q.q[2] = base + b1;
+        return q;
+    };
+    TierQueues cq = regions(g->d_queue[0]), nq = regions(g->d_queue[1]);
+    uint32_t *visited = g->d_part_bm[0], *cur_bm = g->d_part_bm[1], *next_bm = g->d_part_bm[2];
+    PartArgs A;
+    A.col0 = g->col_of_row0;
+    A.vp = vp;
+    A.P = P;
+    A.rank = rank;
+    A.lists = (unsigned long long *)g->d_part_lists;
+    const unsigned long long **d_peer_table = (const unsigned long long **)(ctx->d_counters + 24); // 8 device pointers
+    CUDA_TRY(cudaMemcpyAsync(d_peer_table, g->d_vec_peer, sizeof(g->d_vec_peer), cudaMemcpyHostToDevice, st));
+
+    CUDA_TRY(cudaEventRecord(ctx->ev_start, st));
+    if (rows > 0) CUDA_TRY(cudaMemsetAsync(d_levels, 0xFF, (size_t)rows * 4, st));
+    CUDA_TRY(cudaMemsetAsync(visited, 0, (size_t)words * 4, st));
+    CUDA_TRY(cudaMemsetAsync(cur_bm, 0, (size_t)words * 4, st));
+    CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 2 * C_COUNT * 8, st));
+    const bool own_source = source / vp == rank;
+    const int32_t src_row = own_source ? source - rank * vp : -1;
+    VGLB_REQUIRE(!own_source || src_row < rows, "vglb_bfs: source is a padding column");
+    const int src_tier = src_row < 0 ? 0 : (src_row < b0 ? 0 : (src_row < b1 ? 1 : 2));
+    bfs_part_init_kernel<<<1, 1, 0, st>>>(visited, cur_bm, source, d_levels, src_row, cq.q[src_tier]);
+    KERNEL_TRY();
+    ctx->launches++;
+
+    int32_t n[3] = {0, 0, 0};
+    if (own_source) n[src_tier] = 1;
+    long long n_cur = 1, visited_total = 1;
+    bool bottom_up = false;
+    int32_t level = VGLB_FIRST_LEVEL_VERTEX;
+    int64_t tot_edges = 0, tot_rows = 0, tot_frontier_bytes = 0, levels_run = 0;
+    int32_t bu_levels = 0;
+    const long long Vg = g->V_orig;
+    const long long factor = (g->E_global / (Vg > 0 ? Vg : 1)) / 2 > 0 ? (g->E_global / Vg) / 2 : 1;
+    const int max_blocks = ctx->sm_count * 16;
+    const int big_chunks = (int)ceil_div64(g->max_degree > 0 ? g->max_degree : 1, BFS_BIG_CHUNK);
+    const bool trace = getenv("VGLB_BFS_TRACE") != NULL;
+    double trace_t = 0.0;
+    if (trace)
+    {
+        cudaStreamSynchronize(st);
+        trace_t = trace_now();
+    }
+
+    while (n_cur > 0)
+    {
+        if (!bottom_up)
+        {
+            CUDA_TRY(cudaMemsetAsync(A.lists, 0, (size_t)P * 8, st)); // list lengths (the peers finished reading them: see below)
+            const int blocks_mid = (int)min((int64_t)max_blocks, ceil_div64(n[1], BFS_THREADS / 32));
+            const int blocks_small = (int)min((int64_t)max_blocks, ceil_div64(n[2], BFS_THREADS / BFS_SMALL_LANES));
+            const int64_t grid = (int64_t)n[0] * big_chunks + blocks_mid + blocks_small;
+            if (grid > 0)
+            {
+                bfs_td_kernel<2><<<(unsigned)grid, BFS_THREADS, 0, st>>>(g->d_out_ptr, g->d_out_adj, cq, n[0], big_chunks, n[1], n[2], blocks_mid,
+                                                                       blocks_small, visited, d_levels, level + 1, b0, b1, nq, d_cnt, A);
+                KERNEL_TRY();
+                ctx->launches++;
+            }
+            // barrier: every rank's lists are complete before anybody reads them; they are not reset before every rank has
+            // passed this level's counter allreduce, i.e. finished reading
+            rc = vglb_comm_allreduce_async(comm, d_cnt + 2 * C_COUNT + 2, 1, VGLB_DT_I64, VGLB_OP_SUM);
+            if (rc != VGLB_OK) return rc;
+            bfs_apply_lists_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(d_peer_table, A, g->d_out_ptr, visited, d_levels, level + 1, b0, b1, nq, d_cnt);
+            KERNEL_TRY();
+            ctx->launches++;
+        }
+        else
+        {
+            CUDA_TRY(cudaMemsetAsync(next_bm + my, 0, (size_t)wslice * 4, st));
+            bfs_bu_kernel<<<ctx->sm_count * 8, BFS_THREADS, 0, st>>>(g->d_in_ptr, g->d_in_adj, rows, (const uint32_t *)g->d_scratch_i32, visited + my, cur_bm,
+                                                                    next_bm + my, d_levels, level + 1, d_cnt);
+            KERNEL_TRY();
+            rc = vglb_comm_allgather_async(comm, next_bm, (size_t)wslice * 4);
+            if (rc != VGLB_OK) return rc;
+            bfs_or_kernel<<<(unsigned)min((int64_t)max_blocks, ceil_div64(words, 256)), 256, 0, st>>>(visited, next_bm, words);
+            KERNEL_TRY();
+            ctx->launches += 2;
+            bu_levels++;
+            tot_frontier_bytes += (int64_t)wslice * 4 * 3 + words * 4 * 3;
+        }
+        bfs_copy_counters_kernel<<<1, 32, 0, st>>>(d_cnt);
+        KERNEL_TRY();
+        ctx->launches++;
+        rc = vglb_comm_allreduce_async(comm, d_cnt + C_COUNT, C_COUNT, VGLB_DT_I64, VGLB_OP_SUM);
+        if (rc != VGLB_OK) return rc;
+        CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, 2 * C_COUNT * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 2 * C_COUNT * 8, st));
+        levels_run++;
+        const unsigned long long *gl = h_cnt + C_COUNT; // whole-job sums
+        const int32_t nn[3] = {(int32_t)h_cnt[C_NEXT_BIG], (int32_t)h_cnt[C_NEXT_MID], (int32_t)h_cnt[C_NEXT_SMALL]};
+        const long long n_next = bottom_up ? (long long)gl[C_FOUND] : (long long)(gl[C_NEXT_BIG] + gl[C_NEXT_MID] + gl[C_NEXT_SMALL]);
+        if (trace)
+        {
+            const double now = trace_now();
+            fprintf(stderr, "bfs level %d (%s, rank %d of %d): frontier %lld, this rank inspected %lld edges, found %lld, %.1f us since the previous line\n",
+                    level, bottom_up ? "bottom-up" : "top-down", rank, P, n_cur, (long long)h_cnt[C_EDGES], n_next, (now - trace_t) * 1e6);
+            trace_t = now;
+        }
+        tot_edges += (int64_t)h_cnt[C_EDGES];
+        tot_rows += bottom_up ? (int64_t)h_cnt[C_ROWS] : (int64_t)n[0] + n[1] + n[2];
+        if (!bottom_up) tot_frontier_bytes += 8 * ((int64_t)nn[0] + nn[1] + nn[2]); // queue written now, read next level (+ list entries)
+        visited_total += n_next;
+        if (n_next == 0) break;
+
+        bool next_bu = bottom_up;
+        if (dopt)
+        {
+            const long long unvisited = Vg - visited_total;
+            if (!bottom_up && n_cur < n_next)
+            {
+                if ((long long)gl[C_MF] >= (unvisited * factor + Vg) / alpha) next_bu = true;
+            }
+            else if (bottom_up && n_cur >= n_next)
+            {
+                if (n_next < (unvisited * factor + Vg) / (factor * beta)) next_bu = false;
+            }
+        }
+        if (!bottom_up && !next_bu)
+        {
+            TierQueues t = cq; cq = nq; nq = t;
+            n[0] = nn[0]; n[1] = nn[1]; n[2] = nn[2];
+        }
+        else if (!bottom_up && next_bu)
+        {
+            // the frontier as a replicated bitmap, assembled once from the owners' queues; it is also ORed into every
+            // replica of the visited bitmap (the replicas only knew their own discoveries)
+            CUDA_TRY(cudaMemsetAsync(cur_bm + my, 0, (size_t)wslice * 4, st));
+            const long long nl = (long long)nn[0] + nn[1] + nn[2];
+            if (nl > 0)
+            {
+                bfs_queue_to_bitmap_kernel<<<(unsigned)min((int64_t)max_blocks, ceil_div64(nl, 256)), 256, 0, st>>>(nq, nn[0], nn[1], nn[2], cur_bm + my);
+                KERNEL_TRY();
+            }
+            rc = vglb_comm_allgather_async(comm, cur_bm, (size_t)wslice * 4);
+            if (rc != VGLB_OK) return rc;
+            bfs_or_kernel<<<(unsigned)min((int64_t)max_blocks, ceil_div64(words, 256)), 256, 0, st>>>(visited, cur_bm, words);
+            KERNEL_TRY();
+            ctx->launches += 2;
+            tot_frontier_bytes += words * 4 * 4;
+        }
+        else if (bottom_up && next_bu)
+        {
+            uint32_t *t = cur_bm; cur_bm = next_bm; next_bm = t;
+        }
+        else
+        {
+            bfs_bitmap_to_queue_kernel<<<(unsigned)min((int64_t)max_blocks, ceil_div64(wslice, 256)), 256, 0, st>>>(next_bm + my, rows, b0, b1, cq, d_cnt);
+            KERNEL_TRY();
+            ctx->launches++;
+            CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, 3 * 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            n[0] = (int32_t)h_cnt[0]; n[1] = (int32_t)h_cnt[1]; n[2] = (int32_t)h_cnt[2];
+            CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 2 * C_COUNT * 8, st));
+        }
+        bottom_up = next_bu;
+        n_cur = n_next;
+        level++;
+    }
+    CUDA_TRY(cudaEventRecord(ctx->ev_stop, st));
+    CUDA_TRY(cudaEventSynchronize(ctx->ev_stop));
+    if (stats)
+    {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop));
+        memset(stats, 0, sizeof(*stats));
+        stats->seconds = ms * 1e-3;
+        stats->iterations = levels_run;
+        stats->edges_inspected = tot_edges;      // this rank's
+        stats->vertices_processed = tot_rows;
+        stats->frontier_bytes = tot_frontier_bytes;
+        stats->algorithmic_bytes = 8 * tot_edges + 12 * tot_rows + tot_frontier_bytes;
+        stats->kernel_launches = ctx->launches - launches0;
+        stats->bottom_up_levels = bu_levels;
+    }
+    return VGLB_OK;
+}
+
 static int bfs_prepare(vglb_ctx *ctx, vglb_graph *g)
 {
     if (g->bfs_ready) return VGLB_OK;
@@ -685,7 +1010,14 @@ extern "C" int vglb_bfs(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t *d
                         vglb_stats *stats)
 {
     VGLB_REQUIRE(ctx != NULL && g != NULL && d_levels != NULL, "vglb_bfs: NULL argument");
-    if (g->comm) return bfs_partitioned(ctx, g, source, d_levels, opts, stats);
+    if (g->comm)
+    {
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        int rc = vglb_part_map_lists(ctx, g); // per-owner discovery lists, mapped into the peers once per graph
+        if (rc != VGLB_OK) return rc;
+        return g->vec_peers_mapped > 0 ? bfs_partitioned(ctx, g, source, d_levels, opts, stats)
+                                       : bfs_partitioned_bitmaps(ctx, g, source, d_levels, opts, stats);
+    }
     VGLB_REQUIRE(source >= 0 && source < g->V, "vglb_bfs: source out of range");
     const bool dopt = opts && opts->direction_optimising;
     if (dopt && !g->d_in_ptr)
@@ -751,9 +1083,9 @@ extern "C" int vglb_bfs(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t *d
             const int blocks_mid = (int)min((int64_t)max_blocks, ceil_div64(n[1], BFS_THREADS / 32));
             const int blocks_small = (int)min((int64_t)max_blocks, ceil_div64(n[2], BFS_THREADS / BFS_SMALL_LANES));
             const int64_t grid = (int64_t)n[0] * big_chunks + blocks_mid + blocks_small;
-            bfs_td_kernel<false><<<(unsigned)grid, BFS_THREADS, 0, st>>>(g->d_out_ptr, g->d_out_adj, cq, n[0], big_chunks, n[1], n[2], blocks_mid,
-                                                                 blocks_small, g->d_visited, d_levels, level + 1, b0, b1, nq,
-                                                                 d_cnt);
+            bfs_td_kernel<0><<<(unsigned)grid, BFS_THREADS, 0, st>>>(g->d_out_ptr, g->d_out_adj, cq, n[0], big_chunks, n[1], n[2], blocks_mid,
+                                                                   blocks_small, g->d_visited, d_levels, level + 1, b0, b1, nq, d_cnt,
+                                                                   PartArgs());
             KERNEL_TRY();
             ctx->launches++;
             tot_rows += n_cur;

@@ -161,6 +161,7 @@ int vglb_comm_allgather_async(vglb_comm *comm, void *d_buf, size_t bytes_per_ran
 int vglb_comm_allreduce_async(vglb_comm *comm, void *d_buf, size_t count, int dtype, int op);
 int vglb_comm_alltoall_async(vglb_comm *comm, const void *d_send, void *d_recv, size_t bytes_per_rank);
 int vglb_comm_ipc_map(vglb_comm *comm, void *d_local, void **peers /* [world] */);
+int vglb_part_map_lists(vglb_ctx *ctx, vglb_graph *g);
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

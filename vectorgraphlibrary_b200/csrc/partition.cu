@@ -245,6 +245,26 @@ int vglb_comm_ipc_map(vglb_comm *comm, void *d_local, void **peers)
     return VGLB_OK;
 }
 
+// The per-owner update lists of a partitioned graph (SSSP distance updates, BFS discoveries): P 8-byte counters followed by
+// room for vp entries per owner, mapped into every peer once per graph. A collective: every rank ends up in the same
+// mode — g->vec_peers_mapped = 1 (mapped) or -1 (some rank could not map: the dense / bitmap exchanges are used).
+int vglb_part_map_lists(vglb_ctx *ctx, vglb_graph *g)
+{
+    if (g->vec_peers_mapped != 0) return VGLB_OK;
+    if (!g->d_part_lists) CUDA_TRY(vglb_dev_alloc(&g->d_part_lists, ((size_t)g->cols + g->part_world + 8) * 8));
+    int ok = 1;
+    if (g->part_world > 8 || getenv("VGLB_DENSE_EXCHANGE")) ok = 0;
+    else if (vglb_comm_ipc_map(g->comm, g->d_part_lists, (void **)g->d_vec_peer) != VGLB_OK) ok = 0;
+    int *d_ok = (int *)(ctx->d_counters + 62);
+    CUDA_TRY(cudaMemcpyAsync(d_ok, &ok, 4, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = vglb_comm_allreduce_async(g->comm, d_ok, 1, VGLB_DT_I32, VGLB_OP_MIN);
+    if (rc != VGLB_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(&ok, d_ok, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    g->vec_peers_mapped = ok ? 1 : -1;
+    return VGLB_OK;
+}
+
 extern "C" int vglb_comm_allgather(vglb_comm *comm, void *d_buf, size_t bytes_per_rank)
 {
     VGLB_REQUIRE(comm != NULL && d_buf != NULL, "vglb_comm_allgather: NULL argument");

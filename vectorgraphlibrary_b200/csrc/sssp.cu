@@ -804,22 +804,8 @@ extern "C" int vglb_sssp(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, i
         VGLB_REQUIRE(g->d_bwd != NULL, "vglb_sssp: partitioned graph without a column map");
         CUDA_TRY(cudaSetDevice(ctx->device));
         if (!g->d_part_vec) CUDA_TRY(vglb_dev_alloc(&g->d_part_vec, (size_t)g->cols * 4));
-        // the per-owner update lists of this rank: P counters + vp entries per owner; mapped into the peers once per graph
-        // (every rank must end up in the same mode)
-        if (!g->d_part_lists) CUDA_TRY(vglb_dev_alloc(&g->d_part_lists, ((size_t)g->cols + g->part_world + 8) * 8));
-        if (g->vec_peers_mapped == 0)
-        {
-            int ok = 1;
-            if (g->part_world > 8 || getenv("VGLB_SSSP_DENSE_EXCHANGE")) ok = 0;
-            else if (vglb_comm_ipc_map(g->comm, g->d_part_lists, (void **)g->d_vec_peer) != VGLB_OK) ok = 0;
-            int *d_ok = (int *)(ctx->d_counters + 62);
-            CUDA_TRY(cudaMemcpyAsync(d_ok, &ok, 4, cudaMemcpyHostToDevice, ctx->stream));
-            int rc = vglb_comm_allreduce_async(g->comm, d_ok, 1, VGLB_DT_I32, VGLB_OP_MIN);
-            if (rc != VGLB_OK) return rc;
-            CUDA_TRY(cudaMemcpyAsync(&ok, d_ok, 4, cudaMemcpyDeviceToHost, ctx->stream));
-            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-            g->vec_peers_mapped = ok ? 1 : -1;
-        }
+        int rc = vglb_part_map_lists(ctx, g); // per-owner update lists, mapped into the peers once per graph
+        if (rc != VGLB_OK) return rc;
         if (g->vec_peers_mapped < 0) return sssp_partitioned_dense(ctx, g, d_weights, source, d_dist, stats);
     }
     return sssp_run(ctx, g, d_weights, source, d_dist, stats);
