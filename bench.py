@@ -53,6 +53,20 @@ def host_threads() -> int:
         return os.cpu_count() or 1
 
 
+def ncu_traffic(workload: str, world: int):
+    """DRAM bytes (read + write) of one launch of the dominant kernel from the committed `ncu --set full` summary of this
+    very command (profiles/, B200_PROFILING.md recipe); None where no capture of the configuration exists."""
+    if workload != "pr" or world != 1:
+        return None
+    try:
+        for line in open(os.path.join(ROOT, "profiles", "r1_pr_sweep_ncu_full.txt")):
+            if line.strip().startswith("traffic (dram read + write) bytes:"):
+                return int(line.split(":")[1])
+    except OSError:
+        pass
+    return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -284,7 +298,7 @@ def ours(args):
                        "partition": runner.partition, "l2": "inputs larger than L2 (adjacency %.2f GB per GPU, L2 126 MB)" % (runner.adj_bytes_per_gpu / 1e9),
                        "seed": hex(vgl.MASTER_SEED)},
             "roofline": {"bound": "hbm", "kernel": runner.dominant_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": runner.ncu_traffic, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": ncu_traffic(args.workload, world) if not args.scale else None, "peak_source": peak_src,
                          "bytes_per_launch": kern_bytes, "ms_per_launch": kern_s * 1e3},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
