@@ -55,6 +55,8 @@ struct vglb_ctx
     int sm_count;
     size_t l2_bytes;
     cudaStream_t stream;
+    cudaStream_t copy_stream;   // host -> device uploads that overlap kernels on `stream` (vglb_graph_from_csr)
+    cudaEvent_t ev_chunk[8];
     cudaEvent_t ev_start, ev_stop;
     // host-visible scratch for counters read back once per level / round
     int64_t *h_counters;   // pinned, 64 x int64
@@ -79,6 +81,7 @@ struct vglb_graph
     int32_t tier_degree[VGLB_NUM_TIERS];
     int32_t tier_border[VGLB_NUM_TIERS];
     // lazily created per-algorithm state (owned by the graph, freed with it)
+    int32_t *d_indeg_noloops; // in-degree without self loops, counted while the adjacency is uploaded (vglb_graph_from_csr)
     float *d_pr_inv;       // 1/indeg_noloops (0 when none), SCATTER numbering
     float *d_pr_contrib[2];
     double *d_pr_dangling; // one slot per sweep

@@ -169,6 +169,8 @@ extern "C" int vglb_init(int device, vglb_ctx **out_ctx)
     ctx->sm_count = prop.multiProcessorCount;
     ctx->l2_bytes = (size_t)prop.l2CacheSize;
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; i++) CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreate(&ctx->ev_start));
     CUDA_TRY(cudaEventCreate(&ctx->ev_stop));
     CUDA_TRY(cudaMallocHost((void **)&ctx->h_counters, 64 * sizeof(int64_t)));
@@ -191,6 +193,8 @@ extern "C" int vglb_finalize(vglb_ctx *ctx)
     cudaEventDestroy(ctx->ev_start);
     cudaEventDestroy(ctx->ev_stop);
     cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->copy_stream);
+    for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->ev_chunk[i]);
     free(ctx);
     vglb_dev_cache_release(); // cached blocks of this device go back to the driver
     return VGLB_OK;

@@ -94,6 +94,24 @@ __global__ void gather_adj_kernel(const uint32_t *__restrict__ order, const int3
     }
 }
 
+// in-degree without self loops of the rows [row0, row1) of an out-CSR (one upload chunk of vglb_graph_from_csr)
+__global__ void indegree_noloops_rows_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, int32_t row0, int32_t row1,
+                                             int32_t *__restrict__ indeg)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t v = row0 + warp; v < row1; v += nwarps)
+    {
+        const int64_t s = ptr[v], e = ptr[v + 1];
+        for (int64_t p = s + lane; p < e; p += 32)
+        {
+            const int32_t d = adj[p];
+            if (d != (int32_t)v) atomicAdd(&indeg[d], 1);
+        }
+    }
+}
+
 // in-degree (on the SCATTER numbering) as int64 for the scan
 __global__ void indegree_sorted_kernel(const int32_t *__restrict__ dst, const int32_t *__restrict__ fwd, int64_t E,
                                        unsigned long long *__restrict__ indeg)
@@ -197,7 +215,7 @@ void vglb_graph_free_fields(vglb_graph *g)
         if (g->d_vec_peer[p] && p != g->part_rank) cudaIpcCloseMemHandle(g->d_vec_peer[p]);
     vglb_dev_free(g->d_out_ptr); vglb_dev_free(g->d_out_adj); vglb_dev_free(g->d_in_ptr); vglb_dev_free(g->d_in_adj);
     vglb_dev_free(g->d_fwd); vglb_dev_free(g->d_bwd); vglb_dev_free(g->d_edge_order);
-    vglb_dev_free(g->d_pr_inv); vglb_dev_free(g->d_pr_contrib[0]); vglb_dev_free(g->d_pr_contrib[1]); vglb_dev_free(g->d_pr_dangling); vglb_dev_free(g->d_pr_tasks); vglb_dev_free(g->d_pr_piece_partial); vglb_dev_free(g->d_pr_piece_count); vglb_dev_free(g->d_pr_ve_adj); vglb_dev_free(g->d_pr_ve_ptr);
+    vglb_dev_free(g->d_indeg_noloops); vglb_dev_free(g->d_pr_inv); vglb_dev_free(g->d_pr_contrib[0]); vglb_dev_free(g->d_pr_contrib[1]); vglb_dev_free(g->d_pr_dangling); vglb_dev_free(g->d_pr_tasks); vglb_dev_free(g->d_pr_piece_partial); vglb_dev_free(g->d_pr_piece_count); vglb_dev_free(g->d_pr_ve_adj); vglb_dev_free(g->d_pr_ve_ptr);
     vglb_dev_free(g->d_visited); vglb_dev_free(g->d_front_bm[0]); vglb_dev_free(g->d_front_bm[1]);
     vglb_dev_free(g->d_queue[0]); vglb_dev_free(g->d_queue[1]); vglb_dev_free(g->d_scratch_i32);
 }
@@ -427,21 +445,59 @@ extern "C" int vglb_graph_from_csr(vglb_ctx *ctx, int32_t V, int64_t E, const in
     const size_t eb = (size_t)(E ? E : 1) * 4;
     BUILD_CUDA(vglb_dev_alloc(&g->d_out_ptr, ((size_t)V + 2) * 8));
     BUILD_CUDA(vglb_dev_alloc(&g->d_out_adj, eb + 16));
+    // The upload is PCIe-bound (1.3 GB at ~55 GB/s for the BASELINE PageRank graph), so the device works while it runs: the
+    // adjacency goes up in 8 row-aligned chunks on a second stream and the in-degrees without self loops — what PageRank's
+    // preparation needs first (pr.hpp:28-73), a 7 ms pass of atomics — are counted chunk by chunk behind it.
     BUILD_CUDA(cudaMemcpyAsync(g->d_out_ptr, h_out_ptr, ((size_t)V + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    BUILD_CUDA(cudaMemcpyAsync(g->d_out_adj, h_out_adj, (size_t)E * 4, cudaMemcpyHostToDevice, ctx->stream));
+    BUILD_CUDA(vglb_dev_alloc(&g->d_indeg_noloops, (size_t)V * 4));
+    BUILD_CUDA(cudaMemsetAsync(g->d_indeg_noloops, 0, (size_t)V * 4, ctx->stream));
+    BUILD_CUDA(cudaEventRecord(ctx->ev_chunk[0], ctx->stream));
+    BUILD_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[0], 0)); // (orders the copy stream after earlier work on the buffers)
+    const int chunks = E >= (1 << 22) ? 8 : 1;
+    int32_t row0 = 0;
+    for (int k = 0; k < chunks; k++)
+    {
+        // first row whose edges start at or after the k+1-th eighth of the edge array
+        int32_t row1 = V;
+        if (k + 1 < chunks)
+        {
+            const int64_t target = E / chunks * (k + 1);
+            int32_t lo = row0, hi = V;
+            while (lo < hi)
+            {
+                const int32_t mid = lo + (hi - lo) / 2;
+                if (h_out_ptr[mid] < target) lo = mid + 1;
+                else hi = mid;
+            }
+            row1 = lo;
+        }
+        const int64_t e0 = h_out_ptr[row0], e1 = h_out_ptr[row1];
+        if (e1 > e0)
+        {
+            BUILD_CUDA(cudaMemcpyAsync(g->d_out_adj + e0, h_out_adj + e0, (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+            BUILD_CUDA(cudaEventRecord(ctx->ev_chunk[k], ctx->copy_stream));
+            BUILD_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[k], 0));
+            indegree_noloops_rows_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(g->d_out_ptr, g->d_out_adj, row0, row1, g->d_indeg_noloops);
+            BUILD_CUDA(cudaGetLastError());
+            ctx->launches++;
+        }
+        row0 = row1;
+    }
     if (h_in_ptr)
     {
         BUILD_CUDA(vglb_dev_alloc(&g->d_in_ptr, ((size_t)V + 2) * 8));
         BUILD_CUDA(vglb_dev_alloc(&g->d_in_adj, eb + 16));
-        BUILD_CUDA(cudaMemcpyAsync(g->d_in_ptr, h_in_ptr, ((size_t)V + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-        BUILD_CUDA(cudaMemcpyAsync(g->d_in_adj, h_in_adj, (size_t)E * 4, cudaMemcpyHostToDevice, ctx->stream));
+        BUILD_CUDA(cudaMemcpyAsync(g->d_in_ptr, h_in_ptr, ((size_t)V + 1) * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+        BUILD_CUDA(cudaMemcpyAsync(g->d_in_adj, h_in_adj, (size_t)E * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
     }
     BUILD_CUDA(vglb_dev_alloc(&g->d_fwd, (size_t)V * 4));
     BUILD_CUDA(vglb_dev_alloc(&g->d_bwd, (size_t)V * 4));
     const unsigned vgrid = (unsigned)ceil_div64(V, 256);
     if (h_orig_to_sorted)
-        BUILD_CUDA(cudaMemcpyAsync(g->d_fwd, h_orig_to_sorted, (size_t)V * 4, cudaMemcpyHostToDevice, ctx->stream));
-    else
+        BUILD_CUDA(cudaMemcpyAsync(g->d_fwd, h_orig_to_sorted, (size_t)V * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    BUILD_CUDA(cudaEventRecord(ctx->ev_chunk[0], ctx->copy_stream));
+    BUILD_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[0], 0)); // every upload is ordered before later work on `stream`
+    if (!h_orig_to_sorted)
     {
         iota_kernel<<<vgrid, 256, 0, ctx->stream>>>(g->d_fwd, V);
         BUILD_CUDA(cudaGetLastError());
@@ -662,6 +718,11 @@ extern "C" int vglb_graph_indegree_noloops(vglb_ctx *ctx, vglb_graph *g, int32_t
 {
     VGLB_REQUIRE(ctx != NULL && g != NULL && d_indeg != NULL, "vglb_graph_indegree_noloops: NULL argument");
     VGLB_REQUIRE(g->comm == NULL, "vglb_graph_indegree_noloops: not available on a partitioned graph (in-degrees are counted by the partitioned build)");
+    if (g->d_indeg_noloops) // counted while the graph was uploaded
+    {
+        CUDA_TRY(cudaMemcpyAsync(d_indeg, g->d_indeg_noloops, (size_t)g->V * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        return VGLB_OK;
+    }
     CUDA_TRY(cudaMemsetAsync(d_indeg, 0, (size_t)g->V * 4, ctx->stream));
     indegree_noloops_kernel<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(g->d_out_ptr, g->d_out_adj, g->V, d_indeg);
     KERNEL_TRY();
