@@ -155,6 +155,7 @@ constexpr int32_t vglb_tier_degree(int t)
 int vglb_graph_compute_tiers(vglb_ctx *ctx, vglb_graph *g);
 void vglb_graph_set_unpartitioned(vglb_graph *g);
 int vglb_graph_derive_incoming(vglb_ctx *ctx, vglb_graph *g);
+int vglb_pr_build_tasks_host(vglb_ctx *ctx, vglb_graph *g, const int64_t *h_ptr, int32_t heavy_rows, int32_t long_rows);
 void vglb_graph_free_fields(vglb_graph *g);
 
 // collectives on the context stream (partition.cu); asynchronous, every rank must make the same call

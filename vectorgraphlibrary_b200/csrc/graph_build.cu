@@ -495,6 +495,23 @@ extern "C" int vglb_graph_from_csr(vglb_ctx *ctx, int32_t V, int64_t E, const in
     const unsigned vgrid = (unsigned)ceil_div64(V, 256);
     if (h_orig_to_sorted)
         BUILD_CUDA(cudaMemcpyAsync(g->d_fwd, h_orig_to_sorted, (size_t)V * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (chunks > 1)
+    {
+        // the host is idle while the DMA runs: PageRank's warp-task table of the rows with >= 32 edges (pagerank.cu) is built
+        // from the caller's row pointers now instead of costing 3-4 ms later (rows are degree-sorted: binary search the borders)
+        auto rows_with_degree_at_least = [&](int64_t d) {
+            int32_t lo = 0, hi = V;
+            while (lo < hi)
+            {
+                const int32_t mid = lo + (hi - lo) / 2;
+                if (h_out_ptr[mid + 1] - h_out_ptr[mid] >= d) lo = mid + 1;
+                else hi = mid;
+            }
+            return lo;
+        };
+        BUILD_TRY(vglb_pr_build_tasks_host(ctx, g, h_out_ptr, rows_with_degree_at_least(vglb_tier_degree(1)),
+                                           rows_with_degree_at_least(vglb_tier_degree(0))));
+    }
     BUILD_CUDA(cudaEventRecord(ctx->ev_chunk[0], ctx->copy_stream));
     BUILD_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[0], 0)); // every upload is ordered before later work on `stream`
     if (!h_orig_to_sorted)

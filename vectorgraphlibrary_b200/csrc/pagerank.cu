@@ -387,15 +387,11 @@ __global__ void pr_fill_kernel(float *a, int32_t n, float val)
 // Warp tasks of the heavy region (rows with degree >= 32), built once per graph on the host from the row pointers of
 // that region (a few MB): consecutive rows are packed until ~PR_TASK_EDGES edges or PR_TASK_MAX_ROWS rows; rows with
 // >= PR_PIECE_EDGES edges are cut into pieces.
-static int pr_build_tasks(vglb_ctx *ctx, vglb_graph *g)
+// `h_ptr` = the first heavy_rows + 1 row pointers on the host. vglb_graph_from_csr calls this with the caller's own array while
+// the adjacency DMA is in flight (the host is idle then and the table costs 3-4 ms to build); graphs built on the device
+// copy the pointers of the heavy region down first (pr_build_tasks).
+int vglb_pr_build_tasks_host(vglb_ctx *ctx, vglb_graph *g, const int64_t *ptr, int32_t heavy_rows, int32_t long_rows)
 {
-    const int32_t heavy_rows = g->tier_border[1];
-    std::vector<int64_t> ptr((size_t)heavy_rows + 1);
-    if (heavy_rows > 0)
-    {
-        CUDA_TRY(cudaMemcpyAsync(ptr.data(), g->d_out_ptr, ((size_t)heavy_rows + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    }
     std::vector<PrTask> tasks;
     int32_t slots = 0;
     int32_t r = 0;
@@ -449,11 +445,25 @@ static int pr_build_tasks(vglb_ctx *ctx, vglb_graph *g)
         CUDA_TRY(cudaMemcpyAsync(g->d_pr_tasks, tasks.data(), tasks.size() * sizeof(PrTask), cudaMemcpyHostToDevice, ctx->stream));
     }
     CUDA_TRY(vglb_dev_alloc(&g->d_pr_piece_partial, (size_t)(slots > 0 ? slots : 1) * 4));
-    const size_t counters = (size_t)(g->tier_border[0] > 0 ? g->tier_border[0] : 1);
+    const size_t counters = (size_t)(long_rows > 0 ? long_rows : 1);
     CUDA_TRY(vglb_dev_alloc(&g->d_pr_piece_count, counters * 4));
     CUDA_TRY(cudaMemsetAsync(g->d_pr_piece_count, 0, counters * 4, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return VGLB_OK;
+}
+
+static int pr_build_tasks(vglb_ctx *ctx, vglb_graph *g)
+{
+    const int32_t heavy_rows = g->tier_border[1];
+    std::vector<int64_t> ptr((size_t)heavy_rows + 1);
+    if (heavy_rows > 0)
+    {
+        CUDA_TRY(cudaMemcpyAsync(ptr.data(), g->d_out_ptr, ((size_t)heavy_rows + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    else
+        ptr[0] = 0;
+    return vglb_pr_build_tasks_host(ctx, g, ptr.data(), heavy_rows, g->tier_border[0]);
 }
 
 // ---- padded column-major copy of the tail rows (built once per graph) -------------------------------------------------
@@ -586,7 +596,10 @@ int vglb_pr_prepare(vglb_ctx *ctx, vglb_graph *g, int iters)
         int rc = pr_build_tasks(ctx, g);
         if (rc != VGLB_OK) return rc;
         lap("warp tasks of the heavy rows");
-        rc = pr_build_tail_copy(ctx, g);
+    }
+    if (!g->d_pr_ve_ptr)
+    {
+        int rc = pr_build_tail_copy(ctx, g);
         if (rc != VGLB_OK) return rc;
         lap("padded copy of the tail rows");
     }
