@@ -117,53 +117,59 @@ static int cc_shiloach_vishkin(GraphB200 &graph, GraphAbstractionsB200 &graph_AP
 }
 
 // ---- PageRank, multicore semantics: r'[u] = k + d * (sum_{u->v, v != u} r[v] / indeg_noloops(v) + dangling) ------------
-static void page_rank(GraphB200 &graph, GraphAbstractionsB200 &graph_API, FrontierB200 &frontier, VerticesArrayB200<float> &page_ranks,
-                      int max_iterations)
+// operators used: compute (x4 setup, x1 per sweep), gather (self-loop count over the incoming direction), reduce<float>
+// (dangling mass), scatter in the 8-functor form with a post-op
+static void page_rank(GraphB200 &graph, GraphAbstractionsB200 &graph_API, FrontierB200 &everything, VerticesArrayB200<float> &ranks,
+                      int sweeps)
 {
-    const int vertices_count = graph.get_vertices_count();
-    VerticesArrayB200<int> number_of_loops(graph), incoming_degrees(graph), incoming_degrees_without_loops(graph);
-    VerticesArrayB200<float> reversed_degrees(graph), old_page_ranks(graph);
-    frontier.set_all_active();
+    const int V = graph.get_vertices_count();
+    const float damping = 0.85f;
+    const float teleport = (float)((1.0 - damping) / ((float)V));
+    VerticesArrayB200<int> self_loops(graph), in_degree(graph);
+    VerticesArrayB200<float> inv_in_degree(graph), previous(graph);
+    everything.set_all_active();
+
+    // in-degrees come from the incoming direction: connections_count of a vertex there, minus its self loops
     graph_API.change_traversal_direction(GATHER);
-    auto get_incoming_degrees = [incoming_degrees] __VGLB_COMPUTE_ARGS__ { incoming_degrees[src_id] = connections_count; };
-    graph_API.compute(graph, frontier, get_incoming_degrees);
-    const float d = 0.85f;
-    const float k = (float)((1.0 - d) / ((float)vertices_count));
-    auto init_data = [page_ranks, number_of_loops, vertices_count] __VGLB_COMPUTE_ARGS__ {
-        page_ranks[src_id] = (float)(1.0 / vertices_count);
-        number_of_loops[src_id] = 0;
+    auto start = [ranks, self_loops, in_degree, V] __VGLB_COMPUTE_ARGS__ {
+        ranks[src_id] = (float)(1.0 / V);
+        self_loops[src_id] = 0;
+        in_degree[src_id] = connections_count;
     };
-    graph_API.compute(graph, frontier, init_data);
-    auto calculate_number_of_loops = [number_of_loops] __VGLB_GATHER_ARGS__ {
-        if (src_id == dst_id) atomicAdd(&number_of_loops[src_id], 1);
+    graph_API.compute(graph, everything, start);
+    auto count_self_loops = [self_loops] __VGLB_GATHER_ARGS__ {
+        if (dst_id == src_id) atomicAdd(&self_loops[src_id], 1);
     };
-    graph_API.gather(graph, frontier, calculate_number_of_loops);
-    auto calculate_reversed_degrees = [reversed_degrees, incoming_degrees_without_loops, incoming_degrees, number_of_loops] __VGLB_COMPUTE_ARGS__ {
-        const int deg = incoming_degrees[src_id] - number_of_loops[src_id];
-        incoming_degrees_without_loops[src_id] = deg;
-        reversed_degrees[src_id] = deg == 0 ? 0.0f : (float)(1.0 / deg);
+    graph_API.gather(graph, everything, count_self_loops);
+    auto invert = [inv_in_degree, in_degree, self_loops] __VGLB_COMPUTE_ARGS__ {
+        const int without_loops = in_degree[src_id] - self_loops[src_id];
+        in_degree[src_id] = without_loops;
+        inv_in_degree[src_id] = without_loops > 0 ? (float)(1.0 / without_loops) : 0.0f;
     };
-    graph_API.compute(graph, frontier, calculate_reversed_degrees);
+    graph_API.compute(graph, everything, invert);
     graph_API.change_traversal_direction(SCATTER);
-    for (int it = 0; it < max_iterations; it++)
+
+    for (int sweep = 0; sweep < sweeps; sweep++)
     {
-        auto save_old_ranks = [old_page_ranks, page_ranks] __VGLB_COMPUTE_ARGS__ {
-            old_page_ranks[src_id] = page_ranks[src_id];
-            page_ranks[src_id] = 0;
+        auto shift = [previous, ranks] __VGLB_COMPUTE_ARGS__ {
+            previous[src_id] = ranks[src_id];
+            ranks[src_id] = 0.0f;
         };
-        graph_API.compute(graph, frontier, save_old_ranks);
-        auto reduce_dangling_input = [incoming_degrees_without_loops, old_page_ranks, vertices_count] __VGLB_REDUCE_FLT_ARGS__ {
-            return incoming_degrees_without_loops[src_id] == 0 ? old_page_ranks[src_id] / vertices_count : 0.0f;
+        graph_API.compute(graph, everything, shift);
+        // rank mass of the vertices nobody points to, spread evenly
+        auto dangling_share = [in_degree, previous, V] __VGLB_REDUCE_FLT_ARGS__ {
+            return in_degree[src_id] == 0 ? previous[src_id] / V : 0.0f;
         };
-        const float dangling_input = graph_API.reduce<float>(graph, frontier, reduce_dangling_input, REDUCE_SUM);
-        auto edge_op = [page_ranks, old_page_ranks, reversed_degrees] __VGLB_SCATTER_ARGS__ {
-            if (src_id != dst_id) atomicAdd(&page_ranks[src_id], old_page_ranks[dst_id] * reversed_degrees[dst_id]);
+        const float dangling = graph_API.reduce<float>(graph, everything, dangling_share, REDUCE_SUM);
+        // several lanes work on one row here, so the accumulation into src_id is atomic (VGL_SRC_ID_ADD on the reference GPU)
+        auto pull = [ranks, previous, inv_in_degree] __VGLB_SCATTER_ARGS__ {
+            if (dst_id != src_id) atomicAdd(&ranks[src_id], previous[dst_id] * inv_in_degree[dst_id]);
         };
-        auto vertex_postprocess_op = [page_ranks, k, d, dangling_input] __VGLB_ADVANCE_POSTPROCESS_ARGS__ {
-            page_ranks[src_id] = k + d * (page_ranks[src_id] + dangling_input);
+        auto finish = [ranks, teleport, damping, dangling] __VGLB_ADVANCE_POSTPROCESS_ARGS__ {
+            ranks[src_id] = teleport + damping * (ranks[src_id] + dangling);
         };
-        NoVertexOp EMPTY_VERTEX_OP;
-        graph_API.scatter(graph, frontier, edge_op, EMPTY_VERTEX_OP, vertex_postprocess_op, edge_op, EMPTY_VERTEX_OP, vertex_postprocess_op);
+        NoVertexOp nothing;
+        graph_API.scatter(graph, everything, pull, nothing, finish, pull, nothing, finish);
     }
 }
 

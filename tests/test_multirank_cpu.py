@@ -42,3 +42,21 @@ def test_bench_requires_matching_world_size():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", "2", "--steps", "1"], capture_output=True,
                        text=True, timeout=300, cwd=ROOT)
     assert p.returncode != 0 and "WORLD_SIZE" in (p.stdout + p.stderr)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints one JSON line with the contract's keys;
+    and our own arm refuses to run without a CUDA device instead of falling back to anything."""
+    import json
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--cpu-scale", "12"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "GTEPS" and line["unit"] == "GTEPS" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["gpu_launches"] == 0 and line["config"]["workload"].startswith("PageRank pull")
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1 and "sample" in line["cpu_baseline"]
+    assert line["e2e"] == {"value": line["value"], "unit": "GTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    import torch
+    if not torch.cuda.is_available():
+        q = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+        assert q.returncode != 0 and "no CUDA device" in (q.stdout + q.stderr)
