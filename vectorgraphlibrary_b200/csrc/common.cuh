@@ -119,6 +119,8 @@ struct vglb_graph
     int32_t *d_queue[2];
     int32_t *d_scratch_i32;
     int bfs_ready;
+    int32_t sssp_mid_rows_per_warp; // queue entries of the mid tier per warp (~2048 edges), set with the border
+    int32_t sssp_big_border_plus1; // 0 = not computed yet; else 1 + first id with fewer than 512 edges (sssp.cu)
 };
 
 // NCCL communicator of one rank (partition.cu); the library dlopen()s libnccl.so.2 on first use

@@ -244,6 +244,9 @@ static int sssp_partitioned_dense(vglb_ctx *ctx, vglb_graph *g, const float *d_w
 // mix, loads of one row are consecutive (the queue is ascending, so neighbouring rows are neighbours in memory too),
 // and SSSP_FLAT_UNROLL independent index/weight loads are in flight per lane before the dependent distance gathers.
 #define SSSP_FLAT_UNROLL 4
+#define SSSP_BIG_CHUNK 8192
+#define SSSP_BIG_DEGREE 512  // rows with at least this many edges are relaxed by CTAs (the graph-wide tier border is 4096)
+#define SSSP_WARP_EDGES 1280
 
 // relax one edge: atomicMin on the uint32 view after a plain read that filters the losers; the winner marks the vertex
 // as due in the near (new distance below the threshold) or the far bitmap
@@ -270,7 +273,7 @@ __device__ __forceinline__ void sssp_relax_one(uint32_t *__restrict__ dist, uint
 
 __global__ void __launch_bounds__(SSSP_THREADS)
 sssp_relax_flat_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, const float *__restrict__ wgt,
-                       TierQueues cq, int32_t n_big, int32_t n_mid, int32_t n_small, int32_t per_warp,
+                       TierQueues cq, int32_t n_big, int32_t big_chunks, int32_t n_mid, int32_t n_small, int32_t per_warp_mid, int32_t per_warp,
                        uint32_t *__restrict__ dist, uint32_t *__restrict__ near_bm, uint32_t *__restrict__ far_bm,
                        uint32_t *__restrict__ changed_bm, int32_t col0, int32_t vp, uint32_t threshold_bits,
                        unsigned long long *counters)
@@ -279,35 +282,55 @@ sssp_relax_flat_kernel(const int64_t *__restrict__ ptr, const int32_t *__restric
     const uint64_t pol = l2_policy_evict_first();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     long long edges = 0;
-    if ((int)blockIdx.x < n_big)
+    const int big_blocks = n_big * big_chunks;
+    if ((int)blockIdx.x < big_blocks)
     {
-        // a row with >= 4096 edges: the whole CTA strides it
-        const int32_t u = cq.q[0][blockIdx.x];
-        const int64_t s = ptr[u], e = ptr[u + 1];
+        // a row with >= 4096 edges: one CTA per SSSP_BIG_CHUNK edges (hubs of power-law graphs have 10^5..10^6 edges and are
+        // relaxed again whenever their distance drops), SSSP_FLAT_UNROLL independent edges per thread and step
+        const int32_t u = cq.q[0][blockIdx.x / big_chunks];
+        const int64_t s = ptr[u] + (int64_t)(blockIdx.x % big_chunks) * SSSP_BIG_CHUNK, e = min(ptr[u + 1], s + SSSP_BIG_CHUNK);
+        if (s >= e) return;
         const float du = __uint_as_float(dist[col0 + u]);
         if (threadIdx.x == 0) edges = e - s;
-        for (int64_t p = s + threadIdx.x; p < e; p += SSSP_THREADS)
+        for (int64_t p0 = s + threadIdx.x; p0 < e; p0 += SSSP_THREADS * SSSP_FLAT_UNROLL)
         {
-            const int32_t v = ld_stream_s32(adj + p, pol);
-            const uint32_t c = __float_as_uint(__fadd_rn(du, ld_stream_f32(wgt + p, pol)));
-            sssp_relax_one(dist, near_bm, far_bm, changed_bm, col0, vp, threshold_bits, v, c);
+            int32_t v[SSSP_FLAT_UNROLL];
+            uint32_t c[SSSP_FLAT_UNROLL];
+#pragma unroll
+            for (int k = 0; k < SSSP_FLAT_UNROLL; k++)
+            {
+                const int64_t p = p0 + (int64_t)k * SSSP_THREADS;
+                v[k] = -1;
+                c[k] = 0;
+                if (p < e)
+                {
+                    v[k] = ld_stream_s32(adj + p, pol);
+                    c[k] = __float_as_uint(__fadd_rn(du, ld_stream_f32(wgt + p, pol)));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < SSSP_FLAT_UNROLL; k++)
+                if (v[k] >= 0) sssp_relax_one(dist, near_bm, far_bm, changed_bm, col0, vp, threshold_bits, v[k], c[k]);
         }
     }
     else
     {
-        // per_warp (a power of two <= 32) queue entries per warp: small frontiers are spread over more warps
-        const int batches_mid = (n_mid + per_warp - 1) / per_warp, batches_small = (n_small + per_warp - 1) / per_warp;
-        const int batch = ((int)blockIdx.x - n_big) * (SSSP_THREADS / 32) + warp;
+        // queue entries per warp (powers of two <= 32): few for the mid queue, whose rows have up to SSSP_BIG_DEGREE - 1 edges
+        // each (a warp should not get much more than a few thousand edges), fewer than 32 for the small queue when the
+        // frontier would otherwise leave SMs idle
+        const int batches_mid = (n_mid + per_warp_mid - 1) / per_warp_mid, batches_small = (n_small + per_warp - 1) / per_warp;
+        const int batch = ((int)blockIdx.x - big_blocks) * (SSSP_THREADS / 32) + warp;
         if (batch < batches_mid + batches_small)
         {
             const bool mid = batch < batches_mid;
             const int32_t *q = mid ? cq.q[1] : cq.q[2];
             const int n = mid ? n_mid : n_small;
-            const int i = (mid ? batch : batch - batches_mid) * per_warp + lane;
+            const int pw = mid ? per_warp_mid : per_warp;
+            const int i = (mid ? batch : batch - batches_mid) * pw + lane;
             int64_t s = 0;
             int deg = 0;
             float du = 0.f;
-            if (lane < per_warp && i < n)
+            if (lane < pw && i < n)
             {
                 const int32_t u = q[i];
                 s = ptr[u];
@@ -596,7 +619,24 @@ static int sssp_run(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, int32_
     vglb_comm *comm = g->comm;
     const bool part = comm != NULL;
     const int32_t rows = g->V, vp = part ? g->vp : g->V, col0 = g->col_of_row0, P = g->part_world, rank = g->part_rank;
-    const int32_t b0 = g->tier_border[0], b1 = g->tier_border[1];
+    if (g->sssp_big_border_plus1 == 0) // first id with fewer than SSSP_BIG_DEGREE edges (ids are degree-sorted), once per graph
+    {
+        int32_t border = 0;
+        int rc0 = vglb_graph_threshold_vertex(ctx, g, SSSP_BIG_DEGREE, &border);
+        if (rc0 != VGLB_OK) return rc0;
+        g->sssp_big_border_plus1 = border + 1;
+        // rows of the mid queue (32 <= degree < SSSP_BIG_DEGREE) handed to one warp: about SSSP_WARP_EDGES edges on average
+        const int32_t mid_last = g->tier_border[1] > border ? g->tier_border[1] : border;
+        int64_t pp[2] = {0, 0};
+        CUDA_TRY(cudaMemcpyAsync(&pp[0], g->d_out_ptr + border, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(&pp[1], g->d_out_ptr + mid_last, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        const int64_t avg = mid_last > border ? (pp[1] - pp[0]) / (mid_last - border) : 32;
+        int rows_per_warp = 32;
+        while (rows_per_warp > 1 && rows_per_warp * (avg > 0 ? avg : 1) > SSSP_WARP_EDGES) rows_per_warp >>= 1;
+        g->sssp_mid_rows_per_warp = rows_per_warp;
+    }
+    const int32_t b0 = g->sssp_big_border_plus1 - 1, b1 = g->tier_border[1] > b0 ? g->tier_border[1] : b0;
     const size_t words = ((size_t)vp + 31) / 32;          // bitmaps over this rank's rows
     const int32_t wslice = (int32_t)words;
     const size_t words_full = (size_t)(g->cols + 31) / 32;  // changed bitmap over all columns
@@ -674,7 +714,9 @@ static int sssp_run(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, int32_
     ctx->launches++;
     int64_t tot_edges = 0, tot_rows = 0, tot_next = 0, rounds = 0, selects = 0, far_selects = 0, tot_pulled = 0;
     const unsigned select_grid = (unsigned)ceil_div64((int64_t)words, 256);
-    bool from_far = false;
+    const int big_chunks = (int)ceil_div64(g->max_degree > 0 ? g->max_degree : 1, SSSP_BIG_CHUNK);
+    bool from_far = false, far_nonempty = false;
+    long long tot_queued_global = 0;
     for (;;)
     {
         uint32_t tbits;
@@ -713,16 +755,25 @@ static int sssp_run(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, int32_
                     (long long)h_cnt[C_ROWS], trace_t > 0.0 ? (now - trace_t) * 1e6 : 0.0);
             trace_t = now;
         }
+        if (from_far) far_nonempty = pending > 0;
+        if (from_far && split)
+        {
+            // once most of the graph has been relaxed and little is left, ordering buys nothing and every bucket of the long
+            // tail of distances (power-law graphs) would cost two selections: the rest is relaxed the reference's way
+            const long long Vg = g->V_orig;
+            if (tot_queued_global >= Vg / 2 && n_cur + pending < (Vg / 64 > 4096 ? Vg / 64 : 4096)) threshold = inf;
+        }
         if (n_cur == 0)
         {
             if (!from_far)
             {
-                if (!split) break;      // plain schedule: nothing is ever parked in the far bitmap
+                if (!split || (threshold >= inf && !far_nonempty)) break; // nothing can be parked in the far bitmap any more
                 from_far = true;        // near ran dry: move the threshold and look at the far bitmap
-                threshold += delta;
+                if (threshold < inf) threshold += delta;
                 continue;
             }
             if (pending == 0) break;
+            if (threshold >= inf) continue; // the threshold was just opened: take everything that is pending
             if (part)
             {
                 // the smallest pending distance of the whole job (every rank takes this branch: same allreduced counters)
@@ -741,14 +792,17 @@ static int sssp_run(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, int32_
             continue;
         }
         from_far = false;
+        tot_queued_global += n_cur;
+        if (tbits != 0xffffffffu) far_nonempty = true; // this round relaxes against a finite threshold: it may park vertices
         if (n_local > 0)
         {
             // queue entries per warp: 32 when the frontier is large, fewer when it would leave SMs idle
             int per_warp = 32;
             while (per_warp > 1 && ceil_div64(n[1] + n[2], per_warp) < (int64_t)ctx->sm_count * 32) per_warp >>= 1;
-            const int64_t batches = ceil_div64(n[1], per_warp) + ceil_div64(n[2], per_warp);
-            const int64_t grid = (int64_t)n[0] + ceil_div64(batches, SSSP_THREADS / 32);
-            sssp_relax_flat_kernel<<<(unsigned)grid, SSSP_THREADS, 0, st>>>(g->d_out_ptr, g->d_out_adj, d_weights, cq, n[0], n[1], n[2], per_warp,
+            const int per_warp_mid = per_warp < g->sssp_mid_rows_per_warp ? per_warp : g->sssp_mid_rows_per_warp;
+            const int64_t batches = ceil_div64(n[1], per_warp_mid) + ceil_div64(n[2], per_warp);
+            const int64_t grid = (int64_t)n[0] * big_chunks + ceil_div64(batches, SSSP_THREADS / 32);
+            sssp_relax_flat_kernel<<<(unsigned)grid, SSSP_THREADS, 0, st>>>(g->d_out_ptr, g->d_out_adj, d_weights, cq, n[0], big_chunks, n[1], n[2], per_warp_mid, per_warp,
                                                                            dist, near_bm, far_bm, changed_bm, col0, vp, tbits, d_cnt);
             KERNEL_TRY();
             ctx->launches++;
