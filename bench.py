@@ -303,7 +303,11 @@ def ours(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                     "ms_per_step": e2e["seconds"] * 1e3},
-            "gpu_launches": launches, "clocks": clocks, "extras": runner.extras(),
+            "gpu_launches": launches, "clocks": clocks,
+            # the reference's own "total bandwidth" line: edges x INT_ELEMENTS_PER_EDGE x 4 bytes / time
+            # (apps/bfs/bfs.cpp:3 -> 16 B per edge, apps/pr/pr.cpp:3 etc. -> 20 B; performance_stats.hpp:272-275)
+            "reference_accounting_gbs": edges_per_step * (16 if args.workload == "bfs" else 20) / (ms_per_step * 1e-3) / 1e9,
+            "extras": runner.extras(),
         }
         print(json.dumps(line), flush=True)
     runner.close()
