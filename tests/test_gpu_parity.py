@@ -425,3 +425,83 @@ def test_scale20_properties(vgl, ctx, oracle):
     og = O.OracleGraph(V, dsrc.to_numpy(), ddst.to_numpy())
     assert O.rel_l1(G.to_original(ranks), og.pagerank_f64(20)) <= PR_TOL
     G.free()
+
+
+def test_baseline_size_properties(vgl, ctx, oracle):
+    """BASELINE.json's full single-GPU size (RMAT scale 24, edge factor 16: 268 M edges), checked through properties that
+    do not need an oracle run: the BFS / CC results are the unique solutions of their local equations over the incoming
+    CSR, SSSP satisfies every edge inequality and reaches the BFS set, PageRank conserves mass and one more sweep of the
+    fp64 restatement applied to the 20-sweep result gives the 21-sweep result."""
+    scale, ef = 24, 16
+    V = 1 << scale
+    dsrc, ddst = ctx.generate_edges(vgl.GEN_RMAT, scale, ef)
+    G = vgl.Graph.from_edges(ctx, V, dsrc, ddst, vgl.GRAPH_WITH_INCOMING)
+    dsrc.free(); ddst.free()
+    assert G.E == ef << scale
+    iptr, iadj = G.layout(incoming=True)
+    has_in = np.diff(iptr) > 0
+    starts = iptr[:-1][has_in]  # reduceat over the non-empty in-rows (consecutive non-empty rows are adjacent in iadj)
+
+    def min_over_in_neighbours(values, fill):
+        out = np.full(V, fill, values.dtype)
+        out[has_in] = np.minimum.reduceat(values[iadj], starts)
+        return out
+
+    src_sorted = 0  # the largest hub
+    lv, st_do = G.bfs(src_sorted, direction_optimising=True)
+    a = lv.to_numpy()
+    lv2, st_td = G.bfs(src_sorted, direction_optimising=False)
+    assert np.array_equal(a, lv2.to_numpy()), "levels are direction independent"
+    assert st_do.bottom_up_levels >= 1 and st_do.edges_inspected < st_td.edges_inspected
+    big = np.iinfo(np.int32).max
+    parent_level = min_over_in_neighbours(np.where(a == -1, big, a).astype(np.int32), big)
+    expect = np.where(parent_level == big, -1, parent_level + 1).astype(np.int32)
+    expect[src_sorted] = 1
+    assert np.array_equal(a, expect), "every vertex sits one level below its shallowest in-neighbour"
+    lv.free(); lv2.free()
+
+    lab, _ = G.cc()
+    c = lab.to_numpy()
+    ids = np.arange(V, dtype=np.int32)
+    assert np.array_equal(c, np.minimum(ids, min_over_in_neighbours(c, big))), "labels = min id over the vertex and its in-neighbours' labels"
+    lab.free()
+
+    w = G.synthetic_weights(3)
+    d, _ = G.sssp(w, src_sorted)
+    dn = d.to_numpy()
+    d2, _ = G.sssp(w, src_sorted)
+    assert np.array_equal(dn.view(np.uint32), d2.to_numpy().view(np.uint32)), "SSSP is reproducible bit for bit"
+    fmax = np.finfo(np.float32).max
+    assert np.array_equal(dn < fmax, a != -1), "SSSP and BFS reach the same set"
+    ptr, adj = G.layout()
+    wn = w.to_numpy()
+    for lo in range(0, V, V // 8):  # edge inequalities dist[dst] <= fl(dist[src] + w), an eighth of the rows at a time
+        hi = lo + V // 8
+        e0, e1 = int(ptr[lo]), int(ptr[hi])
+        row = np.repeat(np.arange(lo, hi, dtype=np.int32), np.diff(ptr[lo:hi + 1]))
+        ok = dn[row] < fmax
+        assert np.all(dn[adj[e0:e1][ok]] <= (dn[row[ok]] + wn[e0:e1][ok]).astype(np.float32))
+    del wn
+    w.free(); d.free(); d2.free()
+
+    r20, _ = G.pagerank(20)
+    x = r20.to_numpy().astype(np.float64)
+    assert abs(x.sum() - 1.0) < 1e-5
+    r21, _ = G.pagerank(21)
+    indeg = G.indegree_noloops().to_numpy().astype(np.float64)
+    inv = np.divide(1.0, indeg, out=np.zeros(V), where=indeg > 0)
+    contrib = x * inv
+    sums = np.zeros(V)
+    for lo in range(0, V, V // 8):
+        hi = lo + V // 8
+        e0, e1 = int(ptr[lo]), int(ptr[hi])
+        row = np.repeat(np.arange(lo, hi, dtype=np.int32), np.diff(ptr[lo:hi + 1]))
+        col = adj[e0:e1]
+        vals = np.where(col != row, contrib[col], 0.0)
+        nz = np.diff(ptr[lo:hi + 1]) > 0
+        seg = np.add.reduceat(vals, (ptr[lo:hi][nz] - e0)) if e1 > e0 else np.zeros(0)
+        sums[lo:hi][nz] = seg
+    dangling = x[indeg == 0].sum() / V
+    nxt = (1.0 - 0.85) / V + 0.85 * (sums + dangling)
+    assert oracle.rel_l1(r21.to_numpy(), nxt) <= PR_TOL, "one fp64 sweep on top of the 20-sweep result gives the 21-sweep result"
+    G.free()
