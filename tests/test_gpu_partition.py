@@ -139,3 +139,59 @@ def test_partitioned_drivers_multi_gpu(vgl, world):
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert p.returncode == 0, p.stdout[-4000:] + p.stderr[-4000:]
     assert p.stdout.count("PART_WORKER_OK") == world, p.stdout[-4000:] + p.stderr[-4000:]
+
+
+def test_partitioned_ragged_and_empty(vgl, ctx, oracle):
+    """V not a multiple of 32 or of the rank count, self loops, duplicates, isolated vertices; and a graph without edges."""
+    from vectorgraphlibrary_b200 import multi
+    V = 77
+    rng = np.random.default_rng(5)
+    src = np.concatenate([np.zeros(60, np.int32), rng.integers(1, 50, 90).astype(np.int32), np.array([3, 3, 9], np.int32)])
+    dst = np.concatenate([rng.integers(0, 70, 60).astype(np.int32), rng.integers(0, 50, 90).astype(np.int32), np.array([3, 3, 9], np.int32)])
+    og = oracle.OracleGraph(V, src, dst)
+    for P in (3, 8):
+        vp = multi.rows_per_rank(V, P)
+        seen_rows = 0
+        for rank in range(P):
+            comm = vgl.Comm(ctx, rank, P, detached=True)
+            G = vgl.Graph.from_edges_partitioned(ctx, comm, V, src, dst, vgl.GRAPH_WITH_INCOMING)
+            assert G.V == multi.local_rows(V, P, rank) and G.vp == vp and G.cols == vp * P
+            assert np.array_equal(G.orig_to_sorted(), multi.column_of_sorted(og.fwd, P, vp))
+            ptr, adj = G.layout()
+            for r in range(G.V):
+                s = r * P + rank
+                want = np.sort(multi.column_of_sorted(og.adj[og.row_ptr[s]:og.row_ptr[s + 1]], P, vp))
+                assert np.array_equal(np.sort(adj[ptr[r]:ptr[r + 1]]), want)
+            seen_rows += G.V
+            G.free()
+            comm.close()
+        assert seen_rows == V
+    # live single-rank communicator: the algorithms on the ragged graph and on a graph without edges
+    comm = vgl.Comm(ctx, 0, 1)
+    G = vgl.Graph.from_edges_partitioned(ctx, comm, V, src, dst, vgl.GRAPH_WITH_INCOMING)
+    fwd = G.orig_to_sorted()
+    w = G.synthetic_weights(11)
+    for s in (0, 3, 76):
+        for dopt in (False, True):
+            lv, _ = G.bfs(int(fwd[s]), dopt)
+            assert np.array_equal(G.to_original(lv), og.bfs(s)[0])
+        d, _ = G.sssp(w, int(fwd[s]))
+        assert np.array_equal(G.to_original(d).view(np.uint32), og.sssp(s, 11)[0].view(np.uint32))
+    lab, _ = G.cc()
+    assert np.array_equal(G.to_original(lab), og.cc()[0])
+    ranks, _ = G.pagerank(20)
+    assert oracle.rel_l1(G.to_original(ranks), og.pagerank_f32(20, 2)) <= PR_TOL
+    G.free()
+    e = np.empty(0, np.int32)
+    G0 = vgl.Graph.from_edges_partitioned(ctx, comm, 40, e, e, vgl.GRAPH_WITH_INCOMING)
+    assert G0.E == 0 and G0.V == 40
+    lv, _ = G0.bfs(7, True)
+    exp = np.full(40, -1, np.int32)
+    exp[G0.sorted_to_orig()[7]] = 1
+    assert np.array_equal(G0.to_original(lv), exp)
+    lab, _ = G0.cc()
+    assert np.array_equal(np.sort(G0.to_original(lab)), np.arange(40))
+    ranks, _ = G0.pagerank(3)
+    assert abs(float(ranks.to_numpy().astype(np.float64).sum()) - 1.0) < 1e-5
+    G0.free()
+    comm.close()
