@@ -280,8 +280,11 @@ bfs_apply_lists_kernel(const unsigned long long *const *__restrict__ peer_lists,
 // (the four ids and then the four frontier bits are independent loads), then warp-cooperative scans of the long rows
 // with ballot early exit. Bitmap words are written without atomics; in-rows list sources hubs-first.
 #define BFS_BU_WORDS 4
+#ifndef BFS_BU_MIN_CTAS
+#define BFS_BU_MIN_CTAS 4 // A/B on Kronecker s26: 4 CTAs/SM (60 registers) 1.48-2.02 ms, 5 (48 regs) +3 %, 6 (40 regs, spills) +20 %
+#endif
 
-__global__ void __launch_bounds__(BFS_THREADS)
+__global__ void __launch_bounds__(BFS_THREADS, BFS_BU_MIN_CTAS)
 bfs_bu_kernel(const int64_t *__restrict__ in_ptr, const int32_t *__restrict__ in_adj, int32_t V, const uint32_t *__restrict__ no_in_edges,
               uint32_t *__restrict__ visited, const uint32_t *__restrict__ cur_bm, uint32_t *__restrict__ next_bm,
               int32_t *__restrict__ levels, int32_t next_level, unsigned long long *counters)
