@@ -128,15 +128,19 @@ def test_partitioned_drivers_single_rank_nccl(vgl, ctx, oracle, golden):
     comm.close()
 
 
-@pytest.mark.parametrize("world", [2])
-def test_partitioned_drivers_multi_gpu(vgl, world):
-    """torchrun, one process per GPU; every rank checks the whole result against the golden fixtures."""
+@pytest.mark.parametrize("world,dense", [(2, False), (2, True)])
+def test_partitioned_drivers_multi_gpu(vgl, world, dense):
+    """torchrun, one process per GPU; every rank checks the whole result against the golden fixtures — with the CUDA IPC
+    exchanges (default) and with the NCCL-only fallbacks."""
     if vgl.lib().vglb_device_count() < world:
         pytest.skip(f"needs {world} GPUs (run with gpurun --gpus {world})")
-    port = 29500 + (os.getpid() % 2000)
+    port = 29500 + (os.getpid() % 2000) + (7 if dense else 0)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "part_worker.py")]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    env = dict(os.environ)
+    if dense:
+        env["VGLB_DENSE_EXCHANGE"] = "1"
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
     assert p.returncode == 0, p.stdout[-4000:] + p.stderr[-4000:]
     assert p.stdout.count("PART_WORKER_OK") == world, p.stdout[-4000:] + p.stderr[-4000:]
 
@@ -194,4 +198,18 @@ def test_partitioned_ragged_and_empty(vgl, ctx, oracle):
     ranks, _ = G0.pagerank(3)
     assert abs(float(ranks.to_numpy().astype(np.float64).sum()) - 1.0) < 1e-5
     G0.free()
+    comm.close()
+
+
+def test_partitioned_fallback_exchanges(vgl, ctx, oracle, golden, monkeypatch):
+    """Without CUDA IPC the partitioned BFS / SSSP fall back to NCCL-only exchanges (candidate-bitmap all-to-all,
+    allreduce(min) of the distance vector); VGLB_DENSE_EXCHANGE forces that path."""
+    name, g = golden
+    src, dst = _edges(oracle, g)
+    V = 1 << int(g["scale"])
+    monkeypatch.setenv("VGLB_DENSE_EXCHANGE", "1")
+    comm = vgl.Comm(ctx, 0, 1)
+    G = vgl.Graph.from_edges_partitioned(ctx, comm, V, src, dst, vgl.GRAPH_WITH_INCOMING)
+    _check_algorithms(vgl, ctx, oracle, comm, g, G)
+    G.free()
     comm.close()
