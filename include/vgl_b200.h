@@ -87,7 +87,9 @@ int vglb_graph_from_edges(vglb_ctx *ctx, int32_t vertices, int64_t edges, const 
                           int src_on_device, int flags, vglb_graph **out_graph);
 /* VGL_Graph::move_to_device (vect_csr_graph.hpp:185-196): borrow an already-built VectorCSRGraph (host arrays in
  * sorted numbering: get_vertex_pointers()/get_adjacent_ids(), vect_csr_graph.h:99-100) and copy it to HBM.
- * h_orig_to_sorted (forward_conversion) may be NULL (identity). Incoming arrays may be NULL. */
+ * h_orig_to_sorted (forward_conversion) may be NULL (identity). Incoming arrays may be NULL. The upload is pipelined
+ * (pinned host memory recommended): the adjacency goes up in chunks on a second stream while the in-degrees without self
+ * loops are counted behind it and PageRank's warp-task table is built on the host. All copies have completed on return. */
 int vglb_graph_from_csr(vglb_ctx *ctx, int32_t vertices, int64_t edges, const int64_t *h_out_ptr,
                         const int32_t *h_out_adj, const int32_t *h_orig_to_sorted, const int64_t *h_in_ptr,
                         const int32_t *h_in_adj, vglb_graph **out_graph);
@@ -179,7 +181,9 @@ int vglb_bfs(vglb_ctx *ctx, vglb_graph *g, int32_t source_sorted, int32_t *d_lev
              vglb_stats *stats);
 
 /* SSSP, frontier Bellman-Ford (algorithms/sssp/shortest_paths.hpp:7-78, gpu_shortest_paths.hpp:133-196): min-plus
- * fixed point in fp32, unreachable = FLT_MAX; d_weights indexed by out-CSR position. */
+ * fixed point in fp32 (bit-identical to the reference's seq_dijkstra), unreachable = FLT_MAX; d_weights indexed by
+ * out-CSR position. The frontier is scheduled near/far around a moving distance threshold (fewer re-relaxations than the
+ * reference's "everything that changed" schedule, same fixed point); stats->edges_inspected = edges actually relaxed. */
 int vglb_sssp(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, int32_t source_sorted, float *d_dist,
               vglb_stats *stats);
 
@@ -227,10 +231,11 @@ int vglb_reduce_max_i32(vglb_ctx *ctx, vglb_frontier *f, const int32_t *d_values
  * (vgl_compute_api/common/mpi_exchange.hpp:155-271). Here the GRAPH is partitioned too (the reference replicates it):
  * the degree-sorted ids s = 0..V-1 are dealt round-robin, owner(s) = s mod P, local row = s div P, so every rank owns
  * a degree-sorted slice with ~V/P rows and ~E/P edges (hubs are spread over all ranks). Vertex state is replicated
- * and indexed by COLUMN id = owner * rows_per_rank + local row; each rank computes the slice it owns and the slices
- * are exchanged once per iteration (allgather of owned slices for PageRank contributions / BFS frontier bitmaps,
- * all-to-all OR of candidate bitmaps for top-down BFS, allreduce(min) for SSSP distances / CC labels, allreduce of
- * the convergence counters). vglb_pagerank / vglb_bfs / vglb_sssp / vglb_cc accept a partitioned graph: vertex
+ * and indexed by COLUMN id = owner * rows_per_rank + local row; each rank computes the slice it owns and exchanges once
+ * per iteration: PageRank contributions are stored into the peers' vectors by the sweep itself (CUDA IPC peer memory) or
+ * allgathered; top-down BFS discoveries and SSSP distance updates travel as per-owner lists that the owners read out of
+ * the peers' memory; bottom-up BFS allgathers frontier-bitmap slices; CC allreduces (min) the label vector; a small
+ * allreduce of counters closes every iteration. Without CUDA IPC everything falls back to NCCL collectives. vglb_pagerank / vglb_bfs / vglb_sssp / vglb_cc accept a partitioned graph: vertex
  * outputs then hold THIS RANK's rows (info.vertices entries), `source_sorted` is a column id, and every rank must
  * make the same call (they are collectives). */
 typedef struct vglb_comm vglb_comm;
