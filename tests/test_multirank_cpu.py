@@ -60,3 +60,16 @@ def test_bench_reference_arm_contract():
     if not torch.cuda.is_available():
         q = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
         assert q.returncode != 0 and "no CUDA device" in (q.stdout + q.stderr)
+
+
+def test_source_picker_twins_agree():
+    """dist.pick_sources (bench / runners), oracle.pick_sources (tests) and vglb_source_candidate (include/vglb_synth.h) are the
+    same seeded sequence."""
+    import oracle as O
+    from vectorgraphlibrary_b200 import dist as vdist
+    rng = np.random.default_rng(3)
+    for V in (64, 1000, 1 << 14):
+        deg = rng.integers(0, 3, V)
+        deg[rng.integers(0, V)] = 5
+        for seed in (0xB200, 7):
+            assert vdist.pick_sources(V, deg, 8, seed) == [int(x) for x in O.pick_sources(V, deg, 8, seed)]
