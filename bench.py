@@ -307,6 +307,11 @@ def ours(args):
             # the reference's own "total bandwidth" line: edges x INT_ELEMENTS_PER_EDGE x 4 bytes / time
             # (apps/bfs/bfs.cpp:3 -> 16 B per edge, apps/pr/pr.cpp:3 etc. -> 20 B; performance_stats.hpp:272-275)
             "reference_accounting_gbs": edges_per_step * (16 if args.workload == "bfs" else 20) / (ms_per_step * 1e-3) / 1e9,
+            # BFS / SSSP: one seeded source per step; `value` is the harmonic mean over the timed sources (events
+            # around the whole loop, host gaps between steps included); min / max come from the library's per-call device timers
+            "per_source_gteps": ({"min": edges_per_step / max(s["seconds"] for s in stats) / 1e9,
+                                  "max": edges_per_step / min(s["seconds"] for s in stats) / 1e9, "sources": len(stats)}
+                                 if args.workload in ("bfs", "sssp") else None),
             "extras": runner.extras(),
         }
         print(json.dumps(line), flush=True)
