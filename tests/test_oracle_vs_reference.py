@@ -10,7 +10,7 @@ def _need_ref(O, profile):
         pytest.skip("oracle/_ref not built in this environment")
 
 
-CASES = [(0, 12, 8, 0x1234), (1, 11, 16, 0x77), (2, 11, 32, 0xBEEF)]
+CASES = [(0, 12, 8, 0x1234), (1, 11, 16, 0x77), (2, 11, 32, 0xBEEF), (0, 16, 16, 0xA1), (1, 17, 16, 0xA2), (2, 16, 32, 0xA3)]
 
 
 @pytest.mark.parametrize("kind,scale,ef,seed", CASES)
