@@ -93,6 +93,9 @@ int vglb_graph_from_edges(vglb_ctx *ctx, int32_t vertices, int64_t edges, const 
 int vglb_graph_from_csr(vglb_ctx *ctx, int32_t vertices, int64_t edges, const int64_t *h_out_ptr,
                         const int32_t *h_out_adj, const int32_t *h_orig_to_sorted, const int64_t *h_in_ptr,
                         const int32_t *h_in_adj, vglb_graph **out_graph);
+/* On a partitioned graph whose buffers were mapped by the peers (vglb_graph_set_exchange(P2P), or any BFS / SSSP run over the
+ * per-owner lists) this is a COLLECTIVE: every rank closes its own CUDA IPC mappings, all ranks meet, and only then are the
+ * exported buffers released. Free partitioned graphs on every rank, before vglb_comm_destroy. */
 int vglb_graph_free(vglb_ctx *ctx, vglb_graph *g);
 
 /* ---- the reference's on-disk formats (csrc/graph_io.cu) ----
@@ -167,6 +170,21 @@ typedef struct vglb_stats
 /* PageRank, multicore semantics (algorithms/pr/pr.hpp:7-148): r'[u] = k + d*(sum_{u->v, v!=u} r[v]/indeg_noloops(v) + D).
  * Runs exactly `iters` sweeps; d_ranks (fp32[V]) is returned in SCATTER numbering. */
 int vglb_pagerank(vglb_ctx *ctx, vglb_graph *g, int iters, float damping, float *d_ranks, vglb_stats *stats);
+/* How the dangling mass D is summed. The reference's reduce (pr.hpp:94-103 -> multicore/reduce.hpp:18-31) is an OpenMP static-
+ * chunk fp32 reduction whose rounding error depends on the thread count and exceeds the 1e-6 parity tolerance by orders of
+ * magnitude on large graphs. FP64 (default, what vglb_pagerank does) sums D in double inside the sweep:
+ * within 1e-7 of the exact recurrence. REFERENCE_ORDER replays the reference's summation — `reference_threads` static chunks
+ * of the sorted id range, sequential fp32 inside a chunk, partials added in thread order — so the result is within 1e-6 of
+ * the reference run with OMP_NUM_THREADS = reference_threads (one GPU only; a few ms slower per sweep). */
+#define VGLB_PR_DANGLING_FP64 0
+#define VGLB_PR_DANGLING_REFERENCE_ORDER 1
+typedef struct vglb_pr_opts
+{
+    int32_t dangling_mode;
+    int32_t reference_threads;
+} vglb_pr_opts;
+int vglb_pagerank_ex(vglb_ctx *ctx, vglb_graph *g, int iters, float damping, const vglb_pr_opts *opts, float *d_ranks,
+                     vglb_stats *stats);
 
 /* BFS levels (algorithms/bfs/bfs.hpp:5-86; DO heuristic change_state.hpp:100-141): source = 1, unreachable = -1,
  * SCATTER numbering. direction_optimising needs a graph built WITH_INCOMING. alpha/beta <= 0 select 15 / 18. */

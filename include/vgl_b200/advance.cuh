@@ -80,16 +80,27 @@ __device__ __forceinline__ void advance_row(const CsrView &g, int32_t row, int t
     if (tid == 0) post(row, deg, lane);
 }
 
+// lanes of the warp that form this thread's G-lane row group
+template <int G>
+__device__ __forceinline__ unsigned group_lane_mask()
+{
+    return G >= 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+}
+
 template <int G, class EdgeOp, class PreOp, class PostOp>
 __device__ __forceinline__ void advance_group_rows(const CsrView &g, int32_t row0, int32_t row1, long long edge_shift,
                                                    EdgeOp &edge_op, PreOp &pre, PostOp &post)
 {
     constexpr int GROUPS = kAdvThreads / G;
     const int gid = threadIdx.x / G, gl = threadIdx.x % G;
+    // the G lanes of a group always take the same branch (they share `row`), so the lanes that must meet at the
+    // pre / edges / post barriers are exactly the group's lanes — named explicitly, never __activemask(), which only
+    // reports whoever happens to be converged and would let a lane start its edge ops before lane 0 has run pre()
+    const unsigned group_mask = group_lane_mask<G>();
     for (int32_t base = row0; base < row1; base += GROUPS)
     {
         const int32_t row = base + gid;
-        if (row < row1) advance_row<G>(g, row, gl, edge_shift, edge_op, pre, post, [] { __syncwarp(__activemask()); });
+        if (row < row1) advance_row<G>(g, row, gl, edge_shift, edge_op, pre, post, [group_mask] { __syncwarp(group_mask); });
     }
 }
 
@@ -169,8 +180,9 @@ advance_sparse_kernel(const CsrView g, const SparseFrontierView F, long long edg
         constexpr int GROUPS = kAdvThreads / G;
         const int ngroups = F.blocks_small * GROUPS;
         const int gid = threadIdx.x / G, gl = threadIdx.x % G;
+        const unsigned group_mask = group_lane_mask<G>(); // the loop condition is uniform per group
         for (int i = (b - F.n[0] - F.blocks_mid) * GROUPS + gid; i < F.n[2]; i += ngroups)
-            advance_row<G>(g, F.q[2][i], gl, edge_shift, c_edge_op, c_pre, c_post, [] { __syncwarp(__activemask()); });
+            advance_row<G>(g, F.q[2][i], gl, edge_shift, c_edge_op, c_pre, c_post, [group_mask] { __syncwarp(group_mask); });
     }
 }
 

@@ -49,6 +49,7 @@ def lib() -> C.CDLL:
         L.vglo_bfs.argtypes = [C.c_int32, _i64p, _i32p, C.c_int32, _i32p, C.POINTER(C.c_int64)]
         L.vglo_indegree_noloops.argtypes = [C.c_int32, _i64p, _i32p, _i32p]
         L.vglo_pagerank_f32.argtypes = [C.c_int32, _i64p, _i32p, _i32p, C.c_int, C.c_int, _f32p]
+        L.vglo_pagerank_f32_tree_rows.argtypes = [C.c_int32, _i64p, _i32p, _i32p, C.c_int, C.c_int, _f32p]
         L.vglo_pagerank_f64.argtypes = [C.c_int32, _i64p, _i32p, _i32p, C.c_int, _f64p]
         L.vglo_sssp.argtypes = [C.c_int32, _i64p, _i32p, _f32p, C.c_int32, _f32p, C.POINTER(C.c_int64)]
         L.vglo_sssp_frontier_bf.argtypes = [C.c_int32, _i64p, _i32p, _f32p, C.c_int32, _f32p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
@@ -93,6 +94,20 @@ class OracleGraph:
         if rc != 0:
             raise MemoryError("vglo_build_vect_csr")
 
+    @classmethod
+    def from_csr(cls, row_ptr: np.ndarray, adj: np.ndarray, fwd: np.ndarray | None = None):
+        """Adopt an already-built degree-sorted CSR (e.g. the one the GPU builder produced, downloaded): lets the
+        O(E) oracle algorithms run at sizes where the oracle's own import would take minutes."""
+        self = cls.__new__(cls)
+        self.V, self.E = int(row_ptr.shape[0]) - 1, int(adj.shape[0])
+        self.row_ptr = np.ascontiguousarray(row_ptr, np.int64)
+        self.adj = np.ascontiguousarray(adj, np.int32)
+        self.fwd = np.arange(self.V, dtype=np.int32) if fwd is None else np.ascontiguousarray(fwd, np.int32)
+        self.bwd = np.empty(self.V, np.int32)
+        self.bwd[self.fwd] = np.arange(self.V, dtype=np.int32)
+        self.edge_order = None
+        return self
+
     def thresholds(self, ve_value: int, vc_value: int):
         ve, vc = C.c_int32(), C.c_int32()
         lib().vglo_estimate_thresholds(self.V, self.row_ptr, ve_value, vc_value, C.byref(ve), C.byref(vc))
@@ -120,6 +135,12 @@ class OracleGraph:
     def pagerank_f32(self, iters: int, threads: int):
         r = np.empty(self.V, np.float32)
         lib().vglo_pagerank_f32(self.V, self.row_ptr, self.adj, self.indegree_noloops(), iters, threads, r)
+        return self.to_original(r)
+
+    def pagerank_f32_tree_rows(self, iters: int, threads: int):
+        """fp32 state, reference-order dangling sum over `threads` chunks, fp64-accumulated row sums (see vgl_oracle.c)."""
+        r = np.empty(self.V, np.float32)
+        lib().vglo_pagerank_f32_tree_rows(self.V, self.row_ptr, self.adj, self.indegree_noloops(), iters, threads, r)
         return self.to_original(r)
 
     def pagerank_f64(self, iters: int):
@@ -175,14 +196,19 @@ def pick_sources(V: int, out_degree_orig: np.ndarray, count: int, seed: int = MA
 # Reference (unmodified VGL multicore build) front-end
 # ---------------------------------------------------------------------------------------------------------------------
 
-def ref_available(profile: str = "pr") -> bool:
-    return os.path.exists(os.path.join(_HERE, "_ref", f"libvgl_ref_{profile}.so"))
+def ref_available(profile: str = "pr", timing: bool = False) -> bool:
+    """oracle/_ref holds the unmodified reference compiled for `profile`; timing=True asks for the optimised build
+    (oracle/Makefile TIMING_OPT) that bench.py's CPU arm times, False for the strict-IEEE parity build."""
+    return os.path.exists(os.path.join(_HERE, "_ref", f"libvgl_ref_{profile}{'_timing' if timing else ''}.so"))
 
 
 _REF_LIBS = {}
 
 
-def ref_lib(profile: str) -> C.CDLL:
+def ref_lib(profile: str, timing: bool = False) -> C.CDLL:
+    key = profile
+    if timing:
+        profile = profile + "_timing"
     if profile not in _REF_LIBS:
         if int(os.environ.get("OMP_NUM_THREADS", "2")) < 2:
             raise RuntimeError("the reference segfaults with OMP_NUM_THREADS=1 (SURVEY App. A.1)")
@@ -251,8 +277,8 @@ class RefGraph:
         if self.L.vglref_graph_save(self.h, os.fsencode(path)) != 0:
             raise RuntimeError("VGL_Graph::save_to_binary_file failed")
 
-    def __init__(self, V: int, src: np.ndarray, dst: np.ndarray, profile: str = "pr"):
-        self.L = ref_lib(profile)
+    def __init__(self, V: int, src: np.ndarray, dst: np.ndarray, profile: str = "pr", timing: bool = False):
+        self.L = ref_lib(profile, timing)
         self.V, self.E = V, int(src.shape[0])
         if self.E >= 2 ** 31:
             raise ValueError("the reference cannot process E >= 2^31 (SURVEY App. A.5)")

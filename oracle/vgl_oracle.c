@@ -221,6 +221,58 @@ int vglo_pagerank_f32(int32_t V, const int64_t *row_ptr, const int32_t *adj, con
     return 0;
 }
 
+/* Attribution model of the B200 kernel's "reference-order" mode (vglb_pagerank_ex, dangling_mode = 1): fp32 state and
+ * the reference's T-chunk sequential fp32 dangling sum (above), but every row sum accumulated in fp64 and rounded once
+ * (what a pairwise / tree fp32 sum approaches). Separates the two sources of the reference's fp32 drift:
+ * rel_l1(this, vglo_pagerank_f32) is the row-sum-order share, rel_l1(this, vglo_pagerank_f64) the dangling-sum share. */
+int vglo_pagerank_f32_tree_rows(int32_t V, const int64_t *row_ptr, const int32_t *adj, const int32_t *indeg_noloops,
+                                int iters, int threads, float *ranks)
+{
+    float *old = (float *)malloc((size_t)V * sizeof(float));
+    float *inv = (float *)malloc((size_t)V * sizeof(float));
+    if (!old || !inv) return -1;
+    const float d = 0.85f;
+    const float k = (float)((1.0 - d) / ((float)V));
+    for (int32_t v = 0; v < V; v++)
+    {
+        ranks[v] = (float)(1.0 / V);
+        inv[v] = (float)(1.0 / indeg_noloops[v]);
+        if (indeg_noloops[v] == 0) inv[v] = 0;
+    }
+    if (threads < 1) threads = 1;
+    for (int it = 0; it < iters; it++)
+    {
+        for (int32_t v = 0; v < V; v++) { old[v] = ranks[v]; ranks[v] = 0; }
+        float dangling = 0.0f;
+        {
+            int32_t q = V / threads, t = V % threads;
+            for (int tid = 0; tid < threads; tid++)
+            {
+                int32_t len = q + (tid < t ? 1 : 0);
+                int32_t start = tid < t ? tid * (q + 1) : tid * q + t;
+                float part = 0.0f;
+                for (int32_t v = start; v < start + len; v++)
+                    if (indeg_noloops[v] == 0) part += old[v] / V;
+                dangling += part;
+            }
+        }
+        #pragma omp parallel for schedule(dynamic, 256)
+        for (int32_t u = 0; u < V; u++)
+        {
+            double acc = 0.0;
+            for (int64_t p = row_ptr[u]; p < row_ptr[u + 1]; p++)
+            {
+                int32_t v = adj[p];
+                if (u != v) acc += (double)(old[v] * inv[v]);
+            }
+            ranks[u] = k + d * ((float)acc + dangling);
+        }
+    }
+    free(old);
+    free(inv);
+    return 0;
+}
+
 /* Same recurrence evaluated in fp64 with fp32 constants widened: the attribution reference of SURVEY §8c. */
 int vglo_pagerank_f64(int32_t V, const int64_t *row_ptr, const int32_t *adj, const int32_t *indeg_noloops,
                       int iters, double *ranks)

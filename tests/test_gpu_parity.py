@@ -153,14 +153,29 @@ def test_all_algorithms_vs_oracle(vgl, ctx, oracle, kind, scale, ef, seed):
         d.free()
     lab, _ = G.cc()
     assert np.array_equal(G.to_original(lab), og.cc()[0])
+    # PageRank, the three numbers of SURVEY §8c. The reference sums the dangling mass in fp32 over T static chunks, which
+    # moves its result away from the exact recurrence by far more than the tolerance (1.6e-5 at scale 16, growing with V);
+    # the contract "within 1e-6 of the reference" is met by the reference-order mode (same chunked fp32 dangling sum),
+    # the default mode is within 1e-6 of the exact (fp64) recurrence instead.
+    T = 8
+    r64 = og.pagerank_f64(20)
+    r32 = og.pagerank_f32(20, T)                    # C port of the reference's fp32 evaluation order at T threads
     ranks, _ = G.pagerank(20)
-    r = G.to_original(ranks)
-    assert O.rel_l1(r, og.pagerank_f64(20)) <= PR_TOL
-    # the fp32 oracle in reference order (sequential fp32 row sums, T-chunk fp32 dangling sum) drifts from fp64 truth
-    # as V grows; the contract is checked where the reference itself is within tolerance of truth
-    r32 = og.pagerank_f32(20, 8)
-    if O.rel_l1(r32, og.pagerank_f64(20)) <= 5e-7:
-        assert O.rel_l1(r, r32) <= PR_TOL
+    assert O.rel_l1(G.to_original(ranks), r64) <= PR_TOL
+    ranks_ref, _ = G.pagerank(20, reference_threads=T)
+    r = G.to_original(ranks_ref)
+    numbers = {"ours_vs_reference": O.rel_l1(r, r32), "ours_default_vs_fp64": O.rel_l1(G.to_original(ranks), r64),
+               "reference_vs_fp64": O.rel_l1(r32, r64)}
+    print("PageRank rel-L1", kind, scale, numbers)
+    assert numbers["ours_vs_reference"] <= PR_TOL, numbers
+    if O.ref_available("pr"):                       # the unmodified reference itself, same thread count
+        import os
+        assert int(os.environ.get("OMP_NUM_THREADS", "0")) == T
+        rg = O.RefGraph(V, src, dst, "pr")
+        assert rg.threads() == T
+        rr, _ = rg.pagerank(20)
+        rg.close()
+        assert O.rel_l1(r, rr) <= PR_TOL, ("vs the unmodified reference", O.rel_l1(r, rr), numbers)
     G.free()
 
 

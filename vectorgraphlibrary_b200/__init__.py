@@ -55,6 +55,10 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
 
+class PrOpts(C.Structure):
+    _fields_ = [("dangling_mode", C.c_int32), ("reference_threads", C.c_int32)]
+
+
 class BfsOpts(C.Structure):
     _fields_ = [("direction_optimising", C.c_int32), ("alpha", C.c_int32), ("beta", C.c_int32), ("reserved", C.c_int32)]
 
@@ -97,6 +101,7 @@ _SIGNATURES = {
     "vglb_earray_fill_synthetic_weights": (C.c_int, [_P, _P, C.c_uint64, _P]),
     "vglb_graph_indegree_noloops": (C.c_int, [_P, _P, _P]),
     "vglb_pagerank": (C.c_int, [_P, _P, C.c_int, C.c_float, _P, C.POINTER(Stats)]),
+    "vglb_pagerank_ex": (C.c_int, [_P, _P, C.c_int, C.c_float, C.POINTER(PrOpts), _P, C.POINTER(Stats)]),
     "vglb_bfs": (C.c_int, [_P, _P, C.c_int32, _P, C.POINTER(BfsOpts), C.POINTER(Stats)]),
     "vglb_sssp": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.POINTER(Stats)]),
     "vglb_cc": (C.c_int, [_P, _P, _P, C.POINTER(Stats)]),
@@ -128,6 +133,7 @@ _SIGNATURES = {
 }
 UNIQUE_ID_BYTES = 128
 EXCHANGE_NCCL, EXCHANGE_P2P = 0, 1
+PR_DANGLING_FP64, PR_DANGLING_REFERENCE_ORDER = 0, 1
 
 
 def lib() -> C.CDLL:
@@ -182,13 +188,19 @@ def save_vgl(ctx: "Context", path: str, V: int, src, dst):
 
 
 def pinned_array(n: int, dtype):
-    """numpy view of pinned host memory (vglb_host_alloc_pinned); lives until the process exits."""
+    """numpy view of pinned host memory (vglb_host_alloc_pinned); lives until pinned_free() or the end of the process."""
     dtype = np.dtype(dtype)
     nbytes = max(1, int(n)) * dtype.itemsize
     p = _P()
     _check(lib().vglb_host_alloc_pinned(nbytes, C.byref(p)))
     buf = (C.c_char * nbytes).from_address(p.value)
     return np.frombuffer(buf, dtype=dtype, count=int(n))
+
+
+def pinned_free(arr: np.ndarray):
+    """Release a pinned_array(); the caller must drop every view of it first."""
+    if arr is not None:
+        _check(lib().vglb_host_free_pinned(_P(arr.ctypes.data)))
 
 
 class Context:
@@ -472,10 +484,17 @@ class Graph:
         return d
 
     # ---- the four algorithms ----
-    def pagerank(self, iters: int = 20, damping: float = 0.85, ranks: DeviceArray | None = None):
+    def pagerank(self, iters: int = 20, damping: float = 0.85, ranks: DeviceArray | None = None,
+                 reference_threads: int = 0):
+        """`reference_threads` > 0: sum the dangling mass in the reference's order for that OpenMP thread count
+        (vglb_pagerank_ex, VGLB_PR_DANGLING_REFERENCE_ORDER); 0: fp64 inside the sweep."""
         ranks = ranks or self.ctx.empty(self.V, np.float32)
         st = Stats()
-        _check(lib().vglb_pagerank(self.ctx.h, self.h, iters, damping, ranks.ptr, C.byref(st)))
+        if reference_threads > 0:
+            opts = PrOpts(PR_DANGLING_REFERENCE_ORDER, reference_threads)
+            _check(lib().vglb_pagerank_ex(self.ctx.h, self.h, iters, damping, C.byref(opts), ranks.ptr, C.byref(st)))
+        else:
+            _check(lib().vglb_pagerank(self.ctx.h, self.h, iters, damping, ranks.ptr, C.byref(st)))
         return ranks, st
 
     def bfs(self, source_sorted: int, direction_optimising: bool = True, levels: DeviceArray | None = None,

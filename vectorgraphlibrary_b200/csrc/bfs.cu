@@ -999,12 +999,14 @@ static int bfs_partitioned(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t
 static int bfs_prepare(vglb_ctx *ctx, vglb_graph *g)
 {
     if (g->bfs_ready) return VGLB_OK;
+    // the scratch is shared with SSSP (sssp.cu allocates the same fields, same sizes, on first use): never overwrite
+    // a pointer another algorithm has already filled in
     const size_t words = ((size_t)g->V + 31) / 32 + 32;
-    CUDA_TRY(vglb_dev_alloc(&g->d_visited, words * 4));
-    CUDA_TRY(vglb_dev_alloc(&g->d_front_bm[0], words * 4));
-    CUDA_TRY(vglb_dev_alloc(&g->d_front_bm[1], words * 4));
-    CUDA_TRY(vglb_dev_alloc(&g->d_queue[0], ((size_t)g->V + 3) * 4));
-    CUDA_TRY(vglb_dev_alloc(&g->d_queue[1], ((size_t)g->V + 3) * 4));
+    if (!g->d_visited) CUDA_TRY(vglb_dev_alloc(&g->d_visited, words * 4));
+    if (!g->d_front_bm[0]) CUDA_TRY(vglb_dev_alloc(&g->d_front_bm[0], words * 4));
+    if (!g->d_front_bm[1]) CUDA_TRY(vglb_dev_alloc(&g->d_front_bm[1], words * 4));
+    if (!g->d_queue[0]) CUDA_TRY(vglb_dev_alloc(&g->d_queue[0], ((size_t)g->V + 3) * 4));
+    if (!g->d_queue[1]) CUDA_TRY(vglb_dev_alloc(&g->d_queue[1], ((size_t)g->V + 3) * 4));
     g->bfs_ready = 1;
     return bfs_prepare_no_in_edges(ctx, g);
 }

@@ -64,6 +64,7 @@ struct vglb_ctx
     void *d_flush;         // L2 flush buffer
     size_t flush_bytes;
     int64_t launches;      // kernels launched since the last reset (gpu_launches evidence)
+    int pr_carveout_set;   // pr_sweep_kernel's shared-memory carve-out preference has been set on this device
 };
 
 struct vglb_graph
@@ -114,6 +115,7 @@ struct vglb_graph
     void *d_part_lists;         // SSSP: per-owner lists of (column, distance) updates this rank produced in a round
     uint32_t *d_vec_peer[8];    // the peers' d_part_lists, CUDA IPC mappings (own entry = own buffer)
     int vec_peers_mapped;       // 0 = not tried, 1 = mapped, -1 = mapping failed (dense allreduce exchange is used)
+    int ipc_exported;           // buffers of this graph were offered to the peers over CUDA IPC: vglb_graph_free is a collective
     // BFS / SSSP / CC scratch
     uint32_t *d_visited, *d_front_bm[2];
     int32_t *d_queue[2];

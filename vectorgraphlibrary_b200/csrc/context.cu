@@ -38,8 +38,10 @@ struct DeviceCache
     std::mutex mu;
     std::unordered_map<void *, size_t> live;     // blocks handed out by vglb_dev_alloc
     std::unordered_set<void *> exported;         // never recycled
-    std::multimap<size_t, void *> idle;          // freed blocks by size
+    struct Idle { void *ptr; uint64_t epoch; };
+    std::multimap<size_t, Idle> idle;            // freed blocks by size, with the sync epoch they were freed in
     size_t idle_bytes = 0;
+    uint64_t epoch = 1;                          // bumped by every device-wide synchronisation the cache performs
 };
 DeviceCache &cache_of_current_device()
 {
@@ -62,7 +64,7 @@ size_t cache_limit()
 }
 void cache_release_all(DeviceCache &C)
 {
-    for (auto &kv : C.idle) cudaFree(kv.second);
+    for (auto &kv : C.idle) cudaFree(kv.second.ptr);
     C.idle.clear();
     C.idle_bytes = 0;
 }
@@ -76,7 +78,15 @@ cudaError_t vglb_dev_alloc_bytes(void **ptr, size_t bytes)
     auto it = C.idle.find(bytes);
     if (it != C.idle.end())
     {
-        *ptr = it->second;
+        // Work enqueued before the block was freed may still be using it, and the next user is ordered behind that work
+        // only on the same stream. Freeing does not wait (a graph frees twenty blocks in a row); the first re-use of a
+        // block freed since the last device-wide synchronisation pays for ONE synchronisation that covers them all.
+        if (it->second.epoch == C.epoch)
+        {
+            cudaDeviceSynchronize();
+            C.epoch++;
+        }
+        *ptr = it->second.ptr;
         C.idle.erase(it);
         C.idle_bytes -= bytes;
         C.live[*ptr] = bytes;
@@ -111,15 +121,12 @@ void vglb_dev_free(void *ptr)
         cudaFree(ptr);
         return;
     }
-    // work enqueued on the context streams may still use the block; the next user is ordered behind it only on the same
-    // stream, so wait for the device before the block can be handed to anybody
-    cudaDeviceSynchronize();
-    C.idle.emplace(bytes, ptr);
+    C.idle.emplace(bytes, DeviceCache::Idle{ptr, C.epoch});
     C.idle_bytes += bytes;
     while (C.idle_bytes > cache_limit() && !C.idle.empty())
     {
-        auto big = std::prev(C.idle.end()); // largest first
-        cudaFree(big->second);
+        auto big = std::prev(C.idle.end()); // largest first (cudaFree synchronises by itself)
+        cudaFree(big->second.ptr);
         C.idle_bytes -= big->first;
         C.idle.erase(big);
     }

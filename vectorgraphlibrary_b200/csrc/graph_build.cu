@@ -94,22 +94,48 @@ __global__ void gather_adj_kernel(const uint32_t *__restrict__ order, const int3
     }
 }
 
-// in-degree without self loops of the rows [row0, row1) of an out-CSR (one upload chunk of vglb_graph_from_csr)
+// in-degree without self loops of the rows [row0, row1) of an out-CSR (one upload chunk of vglb_graph_from_csr).
+// The CSR comes from the caller (or from a file): row ranges are clamped to [e_lo, e_hi) — the part of the adjacency
+// this chunk has uploaded — and ids outside [0, V) raise *bad instead of being used as an index.
 __global__ void indegree_noloops_rows_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, int32_t row0, int32_t row1,
-                                             int32_t *__restrict__ indeg)
+                                             int64_t e_lo, int64_t e_hi, int32_t V, int32_t *__restrict__ indeg, int *__restrict__ bad)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t v = row0 + warp; v < row1; v += nwarps)
     {
-        const int64_t s = ptr[v], e = ptr[v + 1];
+        int64_t s = ptr[v], e = ptr[v + 1];
+        if (s < e_lo || e > e_hi || s > e)
+        {
+            if (lane == 0) *bad = 1;
+            continue;
+        }
         for (int64_t p = s + lane; p < e; p += 32)
         {
             const int32_t d = adj[p];
-            if (d != (int32_t)v) atomicAdd(&indeg[d], 1);
+            if ((uint32_t)d >= (uint32_t)V) *bad = 1;
+            else if (d != (int32_t)v) atomicAdd(&indeg[d], 1);
         }
     }
+}
+
+// row pointers of a caller-supplied CSR: ptr[0] == 0, non-decreasing, ptr[rows] == E
+__global__ void csr_ptr_check_kernel(const int64_t *__restrict__ ptr, int32_t rows, int64_t E, int *__restrict__ bad)
+{
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v == 0 && (ptr[0] != 0 || ptr[rows] != E)) *bad = 1;
+    if (v < rows && ptr[v] > ptr[v + 1]) *bad = 1;
+}
+
+// ORIGINAL -> sorted map supplied by the caller: bwd was filled with -1; every slot must be hit exactly once
+__global__ void invert_perm_checked_kernel(const int32_t *__restrict__ fwd, int32_t *__restrict__ bwd, int32_t n, int *__restrict__ bad)
+{
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t f = fwd[i];
+    if ((uint32_t)f >= (uint32_t)n) { *bad = 1; return; }
+    if (atomicExch(&bwd[f], i) != -1) *bad = 1;
 }
 
 // in-degree (on the SCATTER numbering) as int64 for the scan
@@ -204,15 +230,29 @@ int vglb_graph_compute_tiers(vglb_ctx *ctx, vglb_graph *g)
     return VGLB_OK;
 }
 
-void vglb_graph_free_fields(vglb_graph *g)
+// close this process's mappings of the peers' buffers (CUDA IPC)
+static void graph_close_peer_mappings(vglb_graph *g)
 {
-    vglb_dev_free(g->d_part_bm[0]); vglb_dev_free(g->d_part_bm[1]); vglb_dev_free(g->d_part_bm[2]); vglb_dev_free(g->d_part_stage);
-    vglb_dev_free(g->d_part_vec); vglb_dev_free(g->d_part_prev); vglb_dev_free(g->d_part_lists);
     for (int b = 0; b < 2; b++)
         for (int p = 0; p < 8; p++)
-            if (g->d_pr_peer[b][p]) cudaIpcCloseMemHandle(g->d_pr_peer[b][p]);
+            if (g->d_pr_peer[b][p])
+            {
+                cudaIpcCloseMemHandle(g->d_pr_peer[b][p]);
+                g->d_pr_peer[b][p] = NULL;
+            }
     for (int p = 0; p < 8; p++)
-        if (g->d_vec_peer[p] && p != g->part_rank) cudaIpcCloseMemHandle(g->d_vec_peer[p]);
+        if (g->d_vec_peer[p] && p != g->part_rank)
+        {
+            cudaIpcCloseMemHandle(g->d_vec_peer[p]);
+            g->d_vec_peer[p] = NULL;
+        }
+}
+
+void vglb_graph_free_fields(vglb_graph *g)
+{
+    graph_close_peer_mappings(g); // importers close before any exporter frees (vglb_graph_free orders the ranks)
+    vglb_dev_free(g->d_part_bm[0]); vglb_dev_free(g->d_part_bm[1]); vglb_dev_free(g->d_part_bm[2]); vglb_dev_free(g->d_part_stage);
+    vglb_dev_free(g->d_part_vec); vglb_dev_free(g->d_part_prev); vglb_dev_free(g->d_part_lists);
     vglb_dev_free(g->d_out_ptr); vglb_dev_free(g->d_out_adj); vglb_dev_free(g->d_in_ptr); vglb_dev_free(g->d_in_adj);
     vglb_dev_free(g->d_fwd); vglb_dev_free(g->d_bwd); vglb_dev_free(g->d_edge_order);
     vglb_dev_free(g->d_indeg_noloops); vglb_dev_free(g->d_pr_inv); vglb_dev_free(g->d_pr_contrib[0]); vglb_dev_free(g->d_pr_contrib[1]); vglb_dev_free(g->d_pr_dangling); vglb_dev_free(g->d_pr_tasks); vglb_dev_free(g->d_pr_piece_partial); vglb_dev_free(g->d_pr_piece_count); vglb_dev_free(g->d_pr_ve_adj); vglb_dev_free(g->d_pr_ve_ptr);
@@ -225,6 +265,16 @@ extern "C" int vglb_graph_free(vglb_ctx *ctx, vglb_graph *g)
     VGLB_REQUIRE(ctx != NULL, "vglb_graph_free: ctx is NULL");
     if (!g) return VGLB_OK;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (g->ipc_exported && g->comm && g->comm->nccl && g->part_world > 1)
+    {
+        // CUDA leaves cudaFree of an exported buffer undefined while an importer still maps it: every rank first closes
+        // its own mappings, then all ranks meet (one allreduce on the graph's communicator), and only then does anybody
+        // free what it exported. vglb_graph_free is therefore a collective on such a graph, and the graph must be freed
+        // before its communicator is destroyed.
+        graph_close_peer_mappings(g);
+        int rc = vglb_comm_barrier(g->comm);
+        if (rc != VGLB_OK) return rc;
+    }
     vglb_graph_free_fields(g);
     cudaGetLastError();
     free(g);
@@ -442,6 +492,17 @@ extern "C" int vglb_graph_from_csr(vglb_ctx *ctx, int32_t V, int64_t E, const in
     g->V = V;
     g->E = E;
     auto cleanup = [&]() { vglb_graph_free_fields(g); free(g); };
+    // The arrays come from the caller or straight from a .vgl file (vglb_graph_load_vgl): nothing below may index with
+    // a value that has not been checked. Host side: the end points and every chunk border used for a copy; device side
+    // (csr_ptr_check_kernel, the guarded in-degree pass, range_check_kernel, invert_perm_checked_kernel): the rest.
+    if (h_out_ptr[0] != 0 || h_out_ptr[V] != E || (h_in_ptr && (h_in_ptr[0] != 0 || h_in_ptr[V] != E)))
+    {
+        vglb_set_error("vglb_graph_from_csr: row pointers must start at 0 and end at the edge count");
+        cleanup();
+        return VGLB_EINVAL;
+    }
+    int *d_bad = (int *)(ctx->d_counters + 56);
+    BUILD_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
     const size_t eb = (size_t)(E ? E : 1) * 4;
     BUILD_CUDA(vglb_dev_alloc(&g->d_out_ptr, ((size_t)V + 2) * 8));
     BUILD_CUDA(vglb_dev_alloc(&g->d_out_adj, eb + 16));
@@ -451,6 +512,8 @@ extern "C" int vglb_graph_from_csr(vglb_ctx *ctx, int32_t V, int64_t E, const in
     BUILD_CUDA(cudaMemcpyAsync(g->d_out_ptr, h_out_ptr, ((size_t)V + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
     BUILD_CUDA(vglb_dev_alloc(&g->d_indeg_noloops, (size_t)V * 4));
     BUILD_CUDA(cudaMemsetAsync(g->d_indeg_noloops, 0, (size_t)V * 4, ctx->stream));
+    csr_ptr_check_kernel<<<(unsigned)ceil_div64((int64_t)V + 1, 256), 256, 0, ctx->stream>>>(g->d_out_ptr, V, E, d_bad);
+    BUILD_CUDA(cudaGetLastError());
     BUILD_CUDA(cudaEventRecord(ctx->ev_chunk[0], ctx->stream));
     BUILD_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[0], 0)); // (orders the copy stream after earlier work on the buffers)
     const int chunks = E >= (1 << 22) ? 8 : 1;
@@ -472,12 +535,21 @@ extern "C" int vglb_graph_from_csr(vglb_ctx *ctx, int32_t V, int64_t E, const in
             row1 = lo;
         }
         const int64_t e0 = h_out_ptr[row0], e1 = h_out_ptr[row1];
+        if (e0 < 0 || e1 < e0 || e1 > E)
+        {
+            cudaStreamSynchronize(ctx->copy_stream);
+            cudaStreamSynchronize(ctx->stream);
+            vglb_set_error("vglb_graph_from_csr: row pointers are not non-decreasing within [0, E]");
+            cleanup();
+            return VGLB_EINVAL;
+        }
         if (e1 > e0)
         {
             BUILD_CUDA(cudaMemcpyAsync(g->d_out_adj + e0, h_out_adj + e0, (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
             BUILD_CUDA(cudaEventRecord(ctx->ev_chunk[k], ctx->copy_stream));
             BUILD_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[k], 0));
-            indegree_noloops_rows_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(g->d_out_ptr, g->d_out_adj, row0, row1, g->d_indeg_noloops);
+            indegree_noloops_rows_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(g->d_out_ptr, g->d_out_adj, row0, row1, e0, e1, V,
+                                                                                     g->d_indeg_noloops, d_bad);
             BUILD_CUDA(cudaGetLastError());
             ctx->launches++;
         }
@@ -519,11 +591,54 @@ extern "C" int vglb_graph_from_csr(vglb_ctx *ctx, int32_t V, int64_t E, const in
         iota_kernel<<<vgrid, 256, 0, ctx->stream>>>(g->d_fwd, V);
         BUILD_CUDA(cudaGetLastError());
     }
-    invert_perm_kernel<<<vgrid, 256, 0, ctx->stream>>>(g->d_fwd, g->d_bwd, V);
+    BUILD_CUDA(cudaMemsetAsync(g->d_bwd, 0xFF, (size_t)V * 4, ctx->stream));
+    invert_perm_checked_kernel<<<vgrid, 256, 0, ctx->stream>>>(g->d_fwd, g->d_bwd, V, d_bad);
     BUILD_CUDA(cudaGetLastError());
+    if (h_in_ptr)
+    {
+        csr_ptr_check_kernel<<<(unsigned)ceil_div64((int64_t)V + 1, 256), 256, 0, ctx->stream>>>(g->d_in_ptr, V, E, d_bad);
+        BUILD_CUDA(cudaGetLastError());
+        if (E)
+        {
+            range_check_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(g->d_in_adj, E, V, d_bad);
+            BUILD_CUDA(cudaGetLastError());
+        }
+    }
+    int bad = 0;
+    BUILD_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    BUILD_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (bad)
+    {
+        vglb_set_error("vglb_graph_from_csr: not a CSR (row pointers must be non-decreasing from 0 to E, vertex ids in [0, V), "
+                       "the ORIGINAL -> sorted map a permutation)");
+        cleanup();
+        return VGLB_EINVAL;
+    }
     BUILD_TRY(vglb_graph_compute_tiers(ctx, g));
     vglb_graph_set_unpartitioned(g);
     *out_graph = g;
+    return VGLB_OK;
+}
+
+int vglb_csr_validate_device(vglb_ctx *ctx, const int64_t *d_ptr, int32_t rows, int64_t E, const int32_t *d_adj, int64_t id_limit)
+{
+    int *d_bad = (int *)(ctx->d_counters + 56);
+    CUDA_TRY(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+    csr_ptr_check_kernel<<<(unsigned)ceil_div64((int64_t)rows + 1, 256), 256, 0, ctx->stream>>>(d_ptr, rows, E, d_bad);
+    KERNEL_TRY();
+    if (E > 0)
+    {
+        range_check_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_adj, E, (int32_t)id_limit, d_bad);
+        KERNEL_TRY();
+    }
+    int bad = 0;
+    CUDA_TRY(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (bad)
+    {
+        vglb_set_error("not a CSR: row pointers must be non-decreasing from 0 to the edge count and ids in range");
+        return VGLB_EINVAL;
+    }
     return VGLB_OK;
 }
 

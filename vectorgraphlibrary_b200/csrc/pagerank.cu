@@ -378,6 +378,43 @@ __global__ void pr_init_kernel(const float *__restrict__ inv, int32_t V, float r
     }
 }
 
+// ---- "reference order" dangling mass (vglb_pr_opts.dangling_mode = 1) -----------------------------------------------------
+// The reference sums the dangling mass in fp32: reduce<_T>(..., REDUCE_SUM) (pr.hpp:94-103) is an OpenMP
+// `parallel for schedule(static) reduction(+)` over the sorted id range (multicore/reduce.hpp:18-31): T static chunks,
+// sequential fp32 inside a chunk, partials combined in thread order. With ~V/2 terms of size ~1/V^2 that sum is wrong by far
+// more than the 1e-6 parity tolerance (1.6e-5 at scale 16, 2e-3 at scale 22: oracle/vgl_oracle.c, vglo_pagerank_f32_tree_rows),
+// so "within 1e-6 of the reference" is only reachable by summing in the same order. One warp per chunk: the lanes load 32
+// consecutive values, every lane then replays the 32 sequential fp32 additions through shuffles (adding +0 for vertices
+// that are not dangling is exact, as in the reference); a 1-thread kernel combines the T partials in thread order.
+__global__ void pr_dangling_reference_chunks_kernel(const float *__restrict__ rank, const float *__restrict__ inv, int32_t V,
+                                                    float v_as_float, int threads, float *__restrict__ partial)
+{
+    const int lane = threadIdx.x & 31;
+    const int tid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (tid >= threads) return;
+    const int32_t q = V / threads, t = V % threads; // libgomp static schedule: the first V % T chunks are one longer
+    const int32_t len = q + (tid < t ? 1 : 0);
+    const int32_t start = tid < t ? tid * (q + 1) : tid * q + t;
+    float part = 0.0f;
+    for (int32_t base = start; base < start + len; base += 32)
+    {
+        const int32_t v = base + lane;
+        float val = 0.0f;
+        if (v < start + len && inv[v] == 0.0f) val = __fdiv_rn(rank[v], v_as_float);
+        if (!__any_sync(0xffffffffu, val != 0.0f)) continue;
+#pragma unroll
+        for (int l = 0; l < 32; l++) part = __fadd_rn(part, __shfl_sync(0xffffffffu, val, l));
+    }
+    if (lane == 0) partial[tid] = part;
+}
+
+__global__ void pr_dangling_reference_combine_kernel(const float *__restrict__ partial, int threads, double *__restrict__ out)
+{
+    float dangling = 0.0f;
+    for (int t = 0; t < threads; t++) dangling = __fadd_rn(dangling, partial[t]);
+    *out = (double)dangling;
+}
+
 __global__ void pr_fill_kernel(float *a, int32_t n, float val)
 {
     int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -648,11 +685,11 @@ int vglb_pr_launch_sweep(vglb_ctx *ctx, const PrParams &P, int64_t nblocks)
 {
     if (nblocks <= 0) return VGLB_OK;
     // every KB of L1 holds hub contributions: ask for the smallest shared-memory carve-out (64 B static are used)
-    static bool carveout_set = false;
-    if (!carveout_set)
+    // (a function attribute is per device: remembered per context, not per process)
+    if (!ctx->pr_carveout_set)
     {
         CUDA_TRY(cudaFuncSetAttribute(pr_sweep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
-        carveout_set = true;
+        ctx->pr_carveout_set = 1;
     }
     pr_sweep_kernel<<<(unsigned)nblocks, PR_THREADS, 0, ctx->stream>>>(P);
     KERNEL_TRY();
@@ -662,8 +699,19 @@ int vglb_pr_launch_sweep(vglb_ctx *ctx, const PrParams &P, int64_t nblocks)
 
 extern "C" int vglb_pagerank(vglb_ctx *ctx, vglb_graph *g, int iters, float damping, float *d_ranks, vglb_stats *stats)
 {
+    return vglb_pagerank_ex(ctx, g, iters, damping, NULL, d_ranks, stats);
+}
+
+extern "C" int vglb_pagerank_ex(vglb_ctx *ctx, vglb_graph *g, int iters, float damping, const vglb_pr_opts *opts, float *d_ranks,
+                                vglb_stats *stats)
+{
     VGLB_REQUIRE(ctx != NULL && g != NULL && d_ranks != NULL, "vglb_pagerank: NULL argument");
     VGLB_REQUIRE(iters >= 0 && iters < (1 << 20), "vglb_pagerank: bad iteration count");
+    const bool ref_order = opts && opts->dangling_mode == VGLB_PR_DANGLING_REFERENCE_ORDER;
+    const int ref_threads = ref_order ? opts->reference_threads : 0;
+    VGLB_REQUIRE(!opts || opts->dangling_mode == VGLB_PR_DANGLING_FP64 || ref_order, "vglb_pagerank_ex: bad dangling_mode");
+    VGLB_REQUIRE(!ref_order || (ref_threads >= 1 && ref_threads <= 4096), "vglb_pagerank_ex: reference_threads must be in [1, 4096]");
+    VGLB_REQUIRE(!ref_order || !g->comm, "vglb_pagerank_ex: the reference-order dangling sum needs the whole sorted id range (one GPU)");
     CUDA_TRY(cudaSetDevice(ctx->device));
     const int64_t launches0 = ctx->launches;
     int rc = vglb_pr_prepare(ctx, g, iters);
@@ -708,6 +756,19 @@ extern "C" int vglb_pagerank(vglb_ctx *ctx, vglb_graph *g, int iters, float damp
         return vglb_comm_allreduce_async(comm, dangling, 1, VGLB_DT_F64, VGLB_OP_SUM);
     };
 
+    float *d_ref_partial = NULL;
+    if (ref_order) CUDA_TRY(vglb_dev_alloc(&d_ref_partial, (size_t)ref_threads * sizeof(float)));
+    // dangling mass of the rank vector in d_ranks, summed in the reference's order, into dangling slot `slot`
+    auto reference_dangling = [&](int slot) -> int {
+        pr_dangling_reference_chunks_kernel<<<(unsigned)ceil_div64((int64_t)ref_threads * 32, 256), 256, 0, ctx->stream>>>(
+            d_ranks, g->d_pr_inv, V, P.v_as_float, ref_threads, d_ref_partial);
+        KERNEL_TRY();
+        pr_dangling_reference_combine_kernel<<<1, 1, 0, ctx->stream>>>(d_ref_partial, ref_threads, g->d_pr_dangling + slot);
+        KERNEL_TRY();
+        ctx->launches += 2;
+        return VGLB_OK;
+    };
+
     CUDA_TRY(cudaEventRecord(ctx->ev_start, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(g->d_pr_dangling, 0, (size_t)(iters + 1) * sizeof(double), ctx->stream));
     const float r0 = (float)(1.0 / (double)g->V_orig); // pr.hpp:42
@@ -728,12 +789,20 @@ extern "C" int vglb_pagerank(vglb_ctx *ctx, vglb_graph *g, int iters, float damp
         ctx->launches++;
         rc = exchange(g->d_pr_contrib[0], g->d_pr_dangling, false);
         if (rc != VGLB_OK) return rc;
+        if (ref_order && V > 0)
+        {
+            pr_fill_kernel<<<(unsigned)ceil_div64(V, 256), 256, 0, ctx->stream>>>(d_ranks, V, r0);
+            KERNEL_TRY();
+            ctx->launches++;
+            rc = reference_dangling(0); // replaces the fp64 sum pr_init_kernel left in slot 0
+            if (rc != VGLB_OK) return rc;
+        }
     }
     for (int it = 0; it < iters; it++)
     {
         P.contrib_in = g->d_pr_contrib[it & 1];
         P.contrib_out = g->d_pr_contrib[(it + 1) & 1] + col0;
-        P.rank_out = (it == iters - 1) ? d_ranks : NULL;
+        P.rank_out = (it == iters - 1 || ref_order) ? d_ranks : NULL; // reference order: the next dangling sum reads the ranks
         P.dangling_in = g->d_pr_dangling + it;
         P.dangling_out = g->d_pr_dangling + it + 1;
         P.npeers = 0;
@@ -742,6 +811,11 @@ extern "C" int vglb_pagerank(vglb_ctx *ctx, vglb_graph *g, int iters, float damp
                 if (p != g->part_rank) P.peer_out[P.npeers++] = g->d_pr_peer[(it + 1) & 1][p] + col0;
         rc = vglb_pr_launch_sweep(ctx, P, nblocks);
         if (rc != VGLB_OK) return rc;
+        if (ref_order && it < iters - 1)
+        {
+            rc = reference_dangling(it + 1); // replaces the fp64 sum the sweep's epilogue accumulated
+            if (rc != VGLB_OK) return rc;
+        }
         if (it < iters - 1 || p2p)
         {
             // (with peer stores the last sweep still ends in the allreduce: no rank may start its NEXT run — which
@@ -752,6 +826,7 @@ extern "C" int vglb_pagerank(vglb_ctx *ctx, vglb_graph *g, int iters, float damp
     }
     CUDA_TRY(cudaEventRecord(ctx->ev_stop, ctx->stream));
     CUDA_TRY(cudaEventSynchronize(ctx->ev_stop));
+    vglb_dev_free(d_ref_partial);
     if (stats)
     {
         float ms = 0.f;
@@ -783,40 +858,23 @@ extern "C" int vglb_graph_set_exchange(vglb_ctx *ctx, vglb_graph *g, int mode)
     CUDA_TRY(cudaSetDevice(ctx->device));
     if (!g->d_pr_peer[0][(g->part_rank + 1) % g->part_world])
     {
-        int rc = vglb_pr_prepare(ctx, g, 1);
-        if (rc != VGLB_OK) return rc;
+        // Every rank goes through both handle exchanges whatever happens locally (a rank whose preparation failed offers
+        // no buffer, which makes the exchange fail on every rank instead of leaving the peers inside a collective).
+        const int prep = vglb_pr_prepare(ctx, g, 1);
         const int P = g->part_world, rank = g->part_rank;
-        const size_t hb = sizeof(cudaIpcMemHandle_t);
-        cudaIpcMemHandle_t mine[2];
-        vglb_dev_mark_exported(g->d_pr_contrib[0]);
-        vglb_dev_mark_exported(g->d_pr_contrib[1]);
-        CUDA_TRY(cudaIpcGetMemHandle(&mine[0], g->d_pr_contrib[0]));
-        CUDA_TRY(cudaIpcGetMemHandle(&mine[1], g->d_pr_contrib[1]));
-        char *d_all = NULL;
-        CUDA_TRY(vglb_dev_alloc(&d_all, (size_t)P * 2 * hb));
-        CUDA_TRY(cudaMemcpyAsync(d_all + (size_t)rank * 2 * hb, mine, 2 * hb, cudaMemcpyHostToDevice, ctx->stream));
-        rc = vglb_comm_allgather_async(g->comm, d_all, 2 * hb);
-        if (rc != VGLB_OK) { vglb_dev_free(d_all); return rc; }
-        cudaIpcMemHandle_t all[2 * PR_MAX_PEERS];
-        CUDA_TRY(cudaMemcpyAsync(all, d_all, (size_t)P * 2 * hb, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        vglb_dev_free(d_all);
-        for (int p = 0; p < P; p++)
+        void *peers[2][64];
+        int rcs[2];
+        g->ipc_exported = 1;
+        for (int b = 0; b < 2; b++) rcs[b] = vglb_comm_ipc_map(g->comm, prep == VGLB_OK ? (void *)g->d_pr_contrib[b] : NULL, peers[b]);
+        if (prep != VGLB_OK || rcs[0] != VGLB_OK || rcs[1] != VGLB_OK)
         {
-            if (p == rank) continue;
             for (int b = 0; b < 2; b++)
-            {
-                void *ptr = NULL;
-                cudaError_t e = cudaIpcOpenMemHandle(&ptr, all[2 * p + b], cudaIpcMemLazyEnablePeerAccess);
-                if (e != cudaSuccess)
-                {
-                    cudaGetLastError();
-                    vglb_set_error("vglb_graph_set_exchange: cudaIpcOpenMemHandle of rank %d failed: %s", p, cudaGetErrorString(e));
-                    return VGLB_ECUDA;
-                }
-                g->d_pr_peer[b][p] = (float *)ptr;
-            }
+                for (int p = 0; p < P; p++)
+                    if (rcs[b] == VGLB_OK && p != rank && peers[b][p]) cudaIpcCloseMemHandle(peers[b][p]);
+            return prep != VGLB_OK ? prep : rcs[0] != VGLB_OK ? rcs[0] : rcs[1];
         }
+        for (int b = 0; b < 2; b++)
+            for (int p = 0; p < P; p++) g->d_pr_peer[b][p] = p == rank ? NULL : (float *)peers[b][p];
     }
     g->pr_exchange = VGLB_EXCHANGE_P2P;
     return VGLB_OK;

@@ -210,33 +210,89 @@ int vglb_comm_alltoall_async(vglb_comm *comm, const void *d_send, void *d_recv, 
 }
 
 // Map a cudaMalloc'ed buffer of every rank into this process (CUDA IPC; NVLink peer access): peers[q] = rank q's buffer,
-// peers[rank] = d_local. The handles travel through the communicator (an allgather of 64 bytes per rank).
+// peers[rank] = d_local. The handles travel through the communicator (an allgather of 72 bytes per rank).
+// A collective that every rank completes whatever happens locally: a rank that cannot export its buffer still takes
+// part in the allgather (with its slot marked invalid), success is decided only after it, and mappings opened before
+// a later failure are closed again. On failure peers[] is left all-NULL except peers[rank]. The ranks may disagree
+// about the outcome (an open can fail on one rank only); callers agree on it with an allreduce (vglb_part_map_lists).
+struct IpcSlot
+{
+    cudaIpcMemHandle_t handle;
+    int64_t valid;
+};
+
 int vglb_comm_ipc_map(vglb_comm *comm, void *d_local, void **peers)
 {
     DETACHED_CHECK(comm);
     vglb_ctx *ctx = comm->ctx;
     const int P = comm->world, rank = comm->rank;
-    const size_t hb = sizeof(cudaIpcMemHandle_t);
-    cudaIpcMemHandle_t mine;
+    const size_t hb = sizeof(IpcSlot);
+    for (int q = 0; q < P; q++) peers[q] = NULL;
+    peers[rank] = d_local;
+    IpcSlot mine;
+    memset(&mine, 0, sizeof(mine));
+    int local_ok = 1;
+    char local_msg[256] = "";
     vglb_dev_mark_exported(d_local);
-    CUDA_TRY(cudaIpcGetMemHandle(&mine, d_local));
+    cudaError_t e = cudaIpcGetMemHandle(&mine.handle, d_local);
+    if (e != cudaSuccess)
+    {
+        cudaGetLastError();
+        snprintf(local_msg, sizeof(local_msg), "vglb_comm_ipc_map: cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+        memset(&mine, 0, sizeof(mine));
+        local_ok = 0;
+    }
+    mine.valid = local_ok;
     char *d_all = NULL;
-    CUDA_TRY(vglb_dev_alloc(&d_all, (size_t)P * hb));
-    CUDA_TRY(cudaMemcpyAsync(d_all + (size_t)rank * hb, &mine, hb, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = vglb_comm_allgather_async(comm, d_all, hb);
-    if (rc != VGLB_OK) { vglb_dev_free(d_all); return rc; }
-    cudaIpcMemHandle_t all[64];
-    CUDA_TRY(cudaMemcpyAsync(all, d_all, (size_t)P * hb, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    vglb_dev_free(d_all);
+    IpcSlot all[64];
+    memset(all, 0, sizeof(all));
+    // the staging block lives in the context's counter area when it fits (no allocation that could fail before the
+    // collective); 64 ranks x 72 bytes do not, so larger worlds allocate — and still join the allgather on failure
+    static_assert(sizeof(IpcSlot) == 72, "IpcSlot layout");
+    if (vglb_dev_alloc(&d_all, (size_t)P * hb) != cudaSuccess)
+    {
+        cudaGetLastError();
+        d_all = NULL;
+    }
+    int rc = VGLB_OK;
+    if (d_all)
+    {
+        if (cudaMemcpyAsync(d_all + (size_t)rank * hb, &mine, hb, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) local_ok = 0;
+        rc = vglb_comm_allgather_async(comm, d_all, hb);
+        if (rc == VGLB_OK && cudaMemcpyAsync(all, d_all, (size_t)P * hb, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = VGLB_ECUDA;
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = VGLB_ECUDA;
+        vglb_dev_free(d_all);
+    }
+    else
+    {
+        // cannot stage: this rank cannot join the allgather. 72 x P bytes failing to allocate means the device is out of
+        // memory; the peers' next collective will report the mismatch through NCCL's own error path.
+        vglb_set_error("vglb_comm_ipc_map: out of device memory for the handle exchange");
+        return VGLB_ENOMEM;
+    }
+    if (rc != VGLB_OK) return rc;
+    int all_valid = local_ok;
+    for (int q = 0; q < P; q++)
+        if (!all[q].valid) all_valid = 0;
+    if (!all_valid)
+    {
+        vglb_set_error("%s", local_msg[0] ? local_msg : "vglb_comm_ipc_map: a peer could not export its buffer");
+        return VGLB_ECUDA;
+    }
     for (int q = 0; q < P; q++)
     {
-        if (q == rank) { peers[q] = d_local; continue; }
+        if (q == rank) continue;
         void *ptr = NULL;
-        cudaError_t e = cudaIpcOpenMemHandle(&ptr, all[q], cudaIpcMemLazyEnablePeerAccess);
+        e = cudaIpcOpenMemHandle(&ptr, all[q].handle, cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess)
         {
             cudaGetLastError();
+            for (int r = 0; r < q; r++)
+                if (r != rank && peers[r])
+                {
+                    cudaIpcCloseMemHandle(peers[r]);
+                    peers[r] = NULL;
+                }
             vglb_set_error("vglb_comm_ipc_map: cudaIpcOpenMemHandle of rank %d failed: %s", q, cudaGetErrorString(e));
             return VGLB_ECUDA;
         }
@@ -253,8 +309,12 @@ int vglb_part_map_lists(vglb_ctx *ctx, vglb_graph *g)
     if (g->vec_peers_mapped != 0) return VGLB_OK;
     if (!g->d_part_lists) CUDA_TRY(vglb_dev_alloc(&g->d_part_lists, ((size_t)g->cols + g->part_world + 8) * 8));
     int ok = 1;
-    if (g->part_world > 8 || getenv("VGLB_DENSE_EXCHANGE")) ok = 0;
-    else if (vglb_comm_ipc_map(g->comm, g->d_part_lists, (void **)g->d_vec_peer) != VGLB_OK) ok = 0;
+    if (g->part_world > 8 || getenv("VGLB_DENSE_EXCHANGE")) ok = 0; // (the same decision on every rank)
+    else
+    {
+        g->ipc_exported = 1;
+        if (vglb_comm_ipc_map(g->comm, g->d_part_lists, (void **)g->d_vec_peer) != VGLB_OK) ok = 0;
+    }
     int *d_ok = (int *)(ctx->d_counters + 62);
     CUDA_TRY(cudaMemcpyAsync(d_ok, &ok, 4, cudaMemcpyHostToDevice, ctx->stream));
     int rc = vglb_comm_allreduce_async(g->comm, d_ok, 1, VGLB_DT_I32, VGLB_OP_MIN);
@@ -717,10 +777,30 @@ extern "C" int vglb_graph_from_generator_partitioned(vglb_ctx *ctx, vglb_comm *c
 // ---- VGL_Graph::move_to_device for one rank's part (vect_csr_graph.hpp:185-196): host arrays of an already-built part
 //      (this rank's row pointers and adjacency in column ids, the ORIGINAL -> column map) copied to HBM ----------------
 
-__global__ void part_invert_map_kernel(const int32_t *__restrict__ fwd, int32_t V, int32_t *__restrict__ bwd)
+// bwd was filled with -1; a caller-supplied map must send every vertex to a distinct column in [0, cols)
+__global__ void part_invert_map_kernel(const int32_t *__restrict__ fwd, int32_t V, int64_t cols, int32_t *__restrict__ bwd,
+                                       int *__restrict__ bad)
 {
     int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v < V) bwd[fwd[v]] = v;
+    if (v >= V) return;
+    const int32_t c = fwd[v];
+    if (c < 0 || c >= cols) { *bad = 1; return; }
+    if (atomicExch(&bwd[c], v) != -1) *bad = 1;
+}
+
+__global__ void part_ptr_check_kernel(const int64_t *__restrict__ ptr, int32_t rows, int64_t E, int *__restrict__ bad)
+{
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v == 0 && (ptr[0] != 0 || ptr[rows] != E)) *bad = 1;
+    if (v < rows && ptr[v] > ptr[v + 1]) *bad = 1;
+}
+
+__global__ void part_id_check_kernel(const int32_t *__restrict__ ids, int64_t n, int64_t limit, int *__restrict__ bad)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride)
+        if (ids[i] < 0 || ids[i] >= limit) *bad = 1;
 }
 
 extern "C" int vglb_graph_from_csr_partitioned(vglb_ctx *ctx, vglb_comm *comm, int32_t vertices_global, int32_t rows,
@@ -736,7 +816,7 @@ extern "C" int vglb_graph_from_csr_partitioned(vglb_ctx *ctx, vglb_comm *comm, i
     CUDA_TRY(cudaSetDevice(ctx->device));
     const int32_t vp = (int32_t)(((ceil_div64(V, P) + 31) / 32) * 32);
     const int64_t E = h_out_ptr[rows], E_in = h_in_ptr ? h_in_ptr[rows] : 0;
-    VGLB_REQUIRE(E >= 0 && (E == 0 || h_out_adj != NULL), "vglb_graph_from_csr_partitioned: bad sizes");
+    VGLB_REQUIRE(E >= 0 && E_in >= 0 && (E == 0 || h_out_adj != NULL), "vglb_graph_from_csr_partitioned: bad sizes");
     vglb_graph *g = (vglb_graph *)calloc(1, sizeof(vglb_graph));
     if (!g) return VGLB_ENOMEM;
     auto cleanup = [&]() { vglb_graph_free_fields(g); free(g); };
@@ -765,18 +845,47 @@ extern "C" int vglb_graph_from_csr_partitioned(vglb_ctx *ctx, vglb_comm *comm, i
     PBUILD_CUDA(vglb_dev_alloc(&g->d_bwd, (size_t)g->cols * 4));
     PBUILD_CUDA(cudaMemcpyAsync(g->d_fwd, h_orig_to_col, (size_t)V * 4, cudaMemcpyHostToDevice, st));
     PBUILD_CUDA(cudaMemsetAsync(g->d_bwd, 0xFF, (size_t)g->cols * 4, st));
-    part_invert_map_kernel<<<(unsigned)ceil_div64(V, 256), 256, 0, st>>>(g->d_fwd, V, g->d_bwd);
+    // caller-supplied arrays are checked on the device before anything indexes with them (row pointers non-decreasing
+    // from 0 to E, column ids in [0, cols), the map injective); the verdict travels with the edge count so that a
+    // rank with a bad part takes every rank out of the call together instead of leaving the others in a collective
+    int *d_bad = (int *)(ctx->d_counters + 56);
+    PBUILD_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    part_invert_map_kernel<<<(unsigned)ceil_div64(V, 256), 256, 0, st>>>(g->d_fwd, V, g->cols, g->d_bwd, d_bad);
     PBUILD_CUDA(cudaGetLastError());
-    // whole-graph edge count (a collective when the communicator is live)
+    part_ptr_check_kernel<<<(unsigned)ceil_div64((int64_t)rows + 1, 256), 256, 0, st>>>(g->d_out_ptr, rows, E, d_bad);
+    PBUILD_CUDA(cudaGetLastError());
+    if (E > 0) part_id_check_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(g->d_out_adj, E, g->cols, d_bad);
+    if (h_in_ptr)
+    {
+        part_ptr_check_kernel<<<(unsigned)ceil_div64((int64_t)rows + 1, 256), 256, 0, st>>>(g->d_in_ptr, rows, E_in, d_bad);
+        if (E_in > 0) part_id_check_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(g->d_in_adj, E_in, g->cols, d_bad);
+    }
+    PBUILD_CUDA(cudaGetLastError());
+    int bad = 0;
+    PBUILD_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PBUILD_CUDA(cudaStreamSynchronize(st));
+    // whole-graph edge count and the number of ranks with a bad part (a collective when the communicator is live)
     g->E_global = E;
+    int64_t bad_ranks = bad ? 1 : 0;
     if (comm->nccl && P > 1)
     {
         int64_t *d = ctx->d_counters + 50;
-        PBUILD_CUDA(cudaMemcpyAsync(d, &E, 8, cudaMemcpyHostToDevice, st));
-        int rc = vglb_comm_allreduce_async(comm, d, 1, VGLB_DT_I64, VGLB_OP_SUM);
+        const int64_t h2[2] = {E, bad_ranks};
+        int64_t r2[2] = {0, 0};
+        PBUILD_CUDA(cudaMemcpyAsync(d, h2, 16, cudaMemcpyHostToDevice, st));
+        int rc = vglb_comm_allreduce_async(comm, d, 2, VGLB_DT_I64, VGLB_OP_SUM);
         if (rc != VGLB_OK) { cleanup(); return rc; }
-        PBUILD_CUDA(cudaMemcpyAsync(&g->E_global, d, 8, cudaMemcpyDeviceToHost, st));
+        PBUILD_CUDA(cudaMemcpyAsync(r2, d, 16, cudaMemcpyDeviceToHost, st));
         PBUILD_CUDA(cudaStreamSynchronize(st));
+        g->E_global = r2[0];
+        bad_ranks = r2[1];
+    }
+    if (bad_ranks)
+    {
+        vglb_set_error("vglb_graph_from_csr_partitioned: %s part is not a CSR (row pointers non-decreasing from 0 to E, column "
+                       "ids in [0, columns), ORIGINAL -> column map injective)", bad ? "this rank's" : "another rank's");
+        cleanup();
+        return VGLB_EINVAL;
     }
     int rc = vglb_graph_compute_tiers(ctx, g);
     if (rc != VGLB_OK) { cleanup(); return rc; }

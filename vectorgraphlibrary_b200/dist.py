@@ -107,6 +107,7 @@ class SingleGpuRunner:
     weak = True
     partition = "single GPU, whole graph"
     ncu_traffic = None
+    bfs_direction_optimising = True
 
     def __init__(self, vgl, ctx, workload, kind, scale, ef, pr_iters):
         self.vgl, self.ctx, self.workload, self.pr_iters = vgl, ctx, workload, pr_iters
@@ -124,6 +125,7 @@ class SingleGpuRunner:
         self.g = vgl.Graph.from_edges(ctx, V, src, dst, flags)
         src.free(); dst.free()
         self.V_total, self.E_total = self.g.V, self.g.E
+        self.scale = scale
         self.adj_bytes_per_gpu = 4 * self.g.E
         self.dtype = "f32" if workload in ("pr", "sssp") else "int32"
         self.iters_per_step = pr_iters if workload == "pr" else 1
@@ -148,7 +150,7 @@ class SingleGpuRunner:
             _, st = self.g.pagerank(self.pr_iters, 0.85, self.out)
             return _stats(st, self.pr_iters, st.algorithmic_bytes)
         if w == "bfs":
-            _, st = self.g.bfs(self.sources[i % len(self.sources)], True, self.out)
+            _, st = self.g.bfs(self.sources[i % len(self.sources)], self.bfs_direction_optimising, self.out)
         elif w == "sssp":
             _, st = self.g.sssp(self.weights, self.sources[i % len(self.sources)], self.out)
         else:
@@ -199,7 +201,7 @@ class SingleGpuRunner:
             if self.workload == "pr":
                 g.pagerank(self.pr_iters, 0.85, out)
             elif self.workload == "bfs":
-                g.bfs(self.sources[i % len(self.sources)], True, out)
+                g.bfs(self.sources[i % len(self.sources)], self.bfs_direction_optimising, out)
             elif self.workload == "sssp":
                 w = ctx.empty(g.E, np.float32)
                 vgl._check(L.vglb_memcpy_h2d(ctx.h, w.ptr, H["w"].ctypes.data, H["w"].nbytes))
@@ -220,11 +222,18 @@ class SingleGpuRunner:
         return None
 
     def close(self):
+        if self.weights is not None:
+            self.weights.free()
+        self.out.free()
         self.g.free()
+        if self._host:
+            for a in self._host.values():
+                self.vgl.pinned_free(a)
+        self._host = None
 
 
-def make_runner(vgl, ctx, comm, workload, kind, scale, ef, pr_iters):
+def make_runner(vgl, ctx, comm, workload, kind, scale, ef, pr_iters, weak=True, vcomm=None):
     if comm is None or comm.world == 1:
         return SingleGpuRunner(vgl, ctx, workload, kind, scale, ef, pr_iters)
     from .multi import PartitionedRunner
-    return PartitionedRunner(vgl, ctx, comm, workload, kind, scale, ef, pr_iters)
+    return PartitionedRunner(vgl, ctx, comm, workload, kind, scale, ef, pr_iters, weak=weak, vcomm=vcomm)

@@ -43,18 +43,22 @@ class PartitionedRunner:
     """N > 1: rank r owns the rows {s : s mod N == r} of a graph N times the single-GPU workload (weak scaling: scale +
     log2 N, same edge factor), built in place from the counter-based generator (no edge list ever leaves a GPU)."""
 
-    weak = True
     ncu_traffic = None
+    bfs_direction_optimising = True
 
-    def __init__(self, vgl, ctx, comm, workload, kind, scale, ef, pr_iters):
+    def __init__(self, vgl, ctx, comm, workload, kind, scale, ef, pr_iters, weak=True, vcomm=None):
         self.vgl, self.ctx, self.workload, self.pr_iters = vgl, ctx, workload, pr_iters
         self.tcomm = comm  # torch.distributed plumbing (unique id exchange, host barriers)
         world, rank = comm.world, comm.rank
         extra = int(np.log2(world))
         if (1 << extra) != world:
             raise SystemExit("bench.py: --gpus must be a power of two")
-        self.scale = scale + extra
-        self.comm = vgl.Comm(ctx, rank, world, exchange=lambda b: comm.broadcast_bytes(b, vgl.UNIQUE_ID_BYTES, 0))
+        # weak scaling: the graph grows with the GPU count (scale + log2 N, per-GPU work fixed);
+        # strong scaling: the SAME graph at every N (BASELINE config 4 "at 1/2/4/8", the reference's strong_scalability.sh)
+        self.weak = weak
+        self.scale = scale + extra if weak else scale
+        self._own_comm = vcomm is None
+        self.comm = vcomm or vgl.Comm(ctx, rank, world, exchange=lambda b: comm.broadcast_bytes(b, vgl.UNIQUE_ID_BYTES, 0))
         flags = vgl.GRAPH_WITH_INCOMING if workload == "bfs" else 0
         self.g = vgl.Graph.from_generator_partitioned(ctx, self.comm, kind, self.scale, ef, flags, symmetrize=(workload == "cc"))
         g = self.g
@@ -64,7 +68,7 @@ class PartitionedRunner:
         self.V_total, self.E_total = g.V_global, g.E_global
         self.adj_bytes_per_gpu = 4 * g.E
         self.partition = (f"1D vertex partition over {world} GPUs: sorted ids dealt round-robin (owner = id mod {world}), "
-                          f"weak scaling (scale {self.scale}), rank 0 holds {g.V} rows / {g.E} edges"
+                          f"{'weak' if weak else 'strong'} scaling (scale {self.scale}), rank 0 holds {g.V} rows / {g.E} edges"
                           + (f"; PageRank exchange: {self.exchange}" if workload == "pr" else ""))
         self.dtype = "f32" if workload in ("pr", "sssp") else "int32"
         self.iters_per_step = pr_iters if workload == "pr" else 1
@@ -128,7 +132,7 @@ class PartitionedRunner:
             _, st = self.g.pagerank(self.pr_iters, 0.85, self.out)
             return _stats(st, self.pr_iters, st.algorithmic_bytes)
         if w == "bfs":
-            _, st = self.g.bfs(self.sources[i % len(self.sources)], True, self.out)
+            _, st = self.g.bfs(self.sources[i % len(self.sources)], self.bfs_direction_optimising, self.out)
         elif w == "sssp":
             _, st = self.g.sssp(self.weights, self.sources[i % len(self.sources)], self.out)
         else:
@@ -170,7 +174,7 @@ class PartitionedRunner:
             if self.workload == "pr":
                 g.pagerank(self.pr_iters, 0.85, out)
             elif self.workload == "bfs":
-                g.bfs(self.sources[i % len(self.sources)], True, out)
+                g.bfs(self.sources[i % len(self.sources)], self.bfs_direction_optimising, out)
             elif self.workload == "sssp":
                 w = ctx.empty(g.E, np.float32)
                 vgl._check(L.vglb_memcpy_h2d(ctx.h, w.ptr, H["w"].ctypes.data, H["w"].nbytes))
@@ -193,5 +197,13 @@ class PartitionedRunner:
         return {"rows_rank0": self.g.V, "edges_rank0": self.g.E, "columns": self.g.cols}
 
     def close(self):
-        self.g.free()
-        self.comm.close()
+        if self.weights is not None:
+            self.weights.free()
+        self.out.free()
+        self.g.free()  # a collective: mappings closed on every rank before anybody frees what it exported
+        if self._host:
+            for a in self._host.values():
+                self.vgl.pinned_free(a)
+        self._host = None
+        if self._own_comm:
+            self.comm.close()
