@@ -97,6 +97,12 @@ int vglb_graph_from_csr(vglb_ctx *ctx, int32_t vertices, int64_t edges, const in
  * per-owner lists) this is a COLLECTIVE: every rank closes its own CUDA IPC mappings, all ranks meet, and only then are the
  * exported buffers released. Free partitioned graphs on every rank, before vglb_comm_destroy. */
 int vglb_graph_free(vglb_ctx *ctx, vglb_graph *g);
+/* One direction of a VectorCSRGraph that already lives in device-accessible memory (the reference's GPU build keeps
+ * vertex_pointers / adjacent_ids in managed memory, memory_API.hpp:3-15; vect_csr_graph.h:99-100): nothing is copied and the
+ * arrays stay the caller's. Adds the degree-tier borders and a home for frontier objects; VGLB_EUNSORTED if the rows are not
+ * degree-sorted. This is what the drop-in backend (include/vgl_b200/overlay) attaches to each direction of a VGL_Graph. */
+int vglb_graph_borrow_csr(vglb_ctx *ctx, int32_t vertices, int64_t edges, const int64_t *d_ptr, const int32_t *d_adj,
+                          vglb_graph **out_graph);
 
 /* ---- the reference's on-disk formats (csrc/graph_io.cu) ----
  * .el_container: EdgesContainer::save_to_binary_file / load_from_binary_file (graph_generation/edges_container.h:58-99),
@@ -216,6 +222,12 @@ typedef struct vglb_frontier vglb_frontier;
 #define VGLB_FRONTIER_DENSE 1
 #define VGLB_FRONTIER_SPARSE 2
 int vglb_frontier_create(vglb_ctx *ctx, vglb_graph *g, vglb_frontier **out);
+/* the same, with the id list kept in the caller's array of >= vertices ints (the reference frontier's own ids[],
+ * frontier/containers/base_frontier.h:18): compaction writes straight into the object the algorithm holds */
+int vglb_frontier_create_borrowed(vglb_ctx *ctx, vglb_graph *g, int32_t *d_ids, vglb_frontier **out);
+/* FrontierVectorCSR::add_group_of_vertices (modification.hpp:88-145): an ascending, duplicate-free id list becomes the
+ * frontier (only on an empty frontier, like the reference). `ids` may be the frontier's own (borrowed) array. */
+int vglb_frontier_set_ids(vglb_ctx *ctx, vglb_frontier *f, const int32_t *ids, int32_t n, int ids_on_device);
 int vglb_frontier_destroy(vglb_ctx *ctx, vglb_frontier *f);
 int vglb_frontier_set_all_active(vglb_ctx *ctx, vglb_frontier *f);
 int vglb_frontier_clear(vglb_ctx *ctx, vglb_frontier *f);

@@ -24,6 +24,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "../vgl_b200.h"
@@ -178,6 +179,12 @@ public:
     void set_all_active() { check(vglb_frontier_set_all_active(graph.rt.ctx, handle)); }
     void clear() { check(vglb_frontier_clear(graph.rt.ctx, handle)); }
     void add_vertex(int _v) { check(vglb_frontier_add_vertex(graph.rt.ctx, handle, _v)); }
+    // add_group_of_vertices (modification.hpp:88-145): host ids, sorted ascending first like the reference (Sorter::sort)
+    void add_group_of_vertices(int *_vertex_ids, int _number_of_vertices)
+    {
+        std::sort(_vertex_ids, _vertex_ids + _number_of_vertices);
+        check(vglb_frontier_set_ids(graph.rt.ctx, handle, _vertex_ids, _number_of_vertices, 0));
+    }
     vglb_frontier_info get_info() const
     {
         vglb_frontier_info fi;
@@ -198,6 +205,7 @@ class GraphAbstractionsB200
     double *reduce_buffer = nullptr;  // device scalar (the reference keeps a double[V] buffer, graph_abstractions_gpu.hpp:10-17)
     uint32_t *filter_bitmap = nullptr; // output of the filter pass of generate_new_frontier
     int max_blocks;
+    long long hub_edges_ = -1;
 
     CsrView view(bool incoming) const
     {
@@ -206,6 +214,7 @@ class GraphAbstractionsB200
         v.adj = incoming ? graph.info.d_in_adj : graph.info.d_out_adj;
         v.V = graph.info.vertices;
         for (int t = 0; t < kNumTiers; t++) v.tier_border[t] = graph.info.tier_border[t];
+        v.max_degree = graph.info.max_degree;
         return v;
     }
     static void launch_check()
@@ -213,55 +222,57 @@ class GraphAbstractionsB200
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) throw cudaGetErrorString(e); // SAFE_KERNEL_CALL (cuda_error_handling.h:15-27)
     }
+    long long hub_edges() // edges of the rows with >= 4096 edges (row pointer at the first tier border), read once
+    {
+        if (hub_edges_ < 0)
+        {
+            int64_t e = 0;
+            if (graph.info.tier_border[0] > 0) check(vglb_memcpy_d2h(ctx, &e, graph.info.d_out_ptr + graph.info.tier_border[0], sizeof(e)));
+            hub_edges_ = e;
+        }
+        return hub_edges_;
+    }
 
-    template <typename EdgeOperation, typename VertexPreprocessOperation, typename VertexPostprocessOperation,
-              typename CollectiveEdgeOperation, typename CollectiveVertexPreprocessOperation, typename CollectiveVertexPostprocessOperation>
+    template <typename EdgeOperation, typename VertexPreprocessOperation, typename VertexPostprocessOperation>
     void advance_worker(FrontierB200 &_frontier, bool _incoming, EdgeOperation &edge_op, VertexPreprocessOperation &vertex_preprocess_op,
-                        VertexPostprocessOperation &vertex_postprocess_op, CollectiveEdgeOperation &collective_edge_op,
-                        CollectiveVertexPreprocessOperation &collective_vertex_preprocess_op,
-                        CollectiveVertexPostprocessOperation &collective_vertex_postprocess_op)
+                        VertexPostprocessOperation &vertex_postprocess_op)
     {
         const vglb_frontier_info fi = _frontier.get_info();
         const long long edge_shift = _incoming ? graph.info.edges : 0; // EdgesArray segments: [outgoing | incoming]
         if (_incoming)
         {
             if (!graph.info.has_incoming) throw "Error in GraphAbstractionsB200::gather : the graph was built without the incoming direction";
-            // rows of the incoming CSR are not degree-sorted (it shares the SCATTER numbering): warp per row
+            // rows of the incoming CSR are not degree-sorted (it shares the SCATTER numbering): no id range says anything about
+            // in-degrees, so every row is a "small / mid" row of a sparse list — warp batches of 32 rows walked flat, rows with
+            // >= 32 in-edges by the whole warp
             const bool all = fi.sparsity_type == VGLB_FRONTIER_ALL_ACTIVE;
             const int n = all ? graph.info.vertices : fi.size;
             if (n == 0) return;
-            const long long blocks = (n + (kAdvThreads / 32) - 1) / (kAdvThreads / 32);
+            const long long blocks = ((long long)n + kAdvThreads - 1) / kAdvThreads;
             advance_unsorted_kernel<<<(unsigned)(blocks < max_blocks ? blocks : max_blocks), kAdvThreads, 0, stream>>>(
                 view(true), all ? nullptr : fi.d_ids, n, edge_shift, edge_op, vertex_preprocess_op, vertex_postprocess_op);
             launch_check();
             return;
         }
+        const CsrView g = view(false);
         if (fi.sparsity_type == VGLB_FRONTIER_ALL_ACTIVE)
         {
-            const CsrView g = view(false);
-            const AllActivePlan plan = plan_all_active(g);
+            const AllActivePlan plan = plan_all_active<VertexPreprocessOperation, VertexPostprocessOperation>(g, graph.info.edges, hub_edges());
             if (plan.blocks == 0) return;
-            advance_all_active_kernel<<<(unsigned)plan.blocks, kAdvThreads, 0, stream>>>(
-                g, plan, edge_shift, edge_op, vertex_preprocess_op, vertex_postprocess_op, collective_edge_op,
-                collective_vertex_preprocess_op, collective_vertex_postprocess_op);
+            advance_all_active_kernel<<<(unsigned)plan.blocks, kAdvThreads, 0, stream>>>(g, plan, edge_shift, edge_op, vertex_preprocess_op,
+                                                                                       vertex_postprocess_op);
             launch_check();
             return;
         }
         // DENSE and SPARSE: the ascending id list; its tiers are contiguous prefixes because ids are degree-sorted
         if (fi.size == 0) return;
         SparseFrontierView F;
-        F.q[0] = fi.d_ids;
-        F.q[1] = fi.d_ids + fi.tier_size[0];
-        F.q[2] = fi.d_ids + fi.tier_size[0] + fi.tier_size[1];
-        for (int t = 0; t < 3; t++) F.n[t] = fi.tier_size[t];
-        const long long bm = (F.n[1] + (kAdvThreads / 32) - 1) / (kAdvThreads / 32), bs = (F.n[2] + (kAdvThreads / 8) - 1) / (kAdvThreads / 8);
-        F.blocks_mid = (int)(bm < max_blocks ? bm : max_blocks);
-        F.blocks_small = (int)(bs < max_blocks ? bs : max_blocks);
-        const long long grid = (long long)F.n[0] + F.blocks_mid + F.blocks_small;
-        advance_sparse_kernel<<<(unsigned)grid, kAdvThreads, 0, stream>>>(view(false), F, edge_shift, edge_op, vertex_preprocess_op,
-                                                                         vertex_postprocess_op, collective_edge_op,
-                                                                         collective_vertex_preprocess_op,
-                                                                         collective_vertex_postprocess_op);
+        F.ids = fi.d_ids;
+        F.n_hub = fi.tier_size[0];
+        F.n_mid = fi.tier_size[1];
+        F.n_small = fi.tier_size[2];
+        const long long grid = plan_sparse<VertexPreprocessOperation, VertexPostprocessOperation>(g, F, max_blocks);
+        advance_sparse_kernel<<<(unsigned)grid, kAdvThreads, 0, stream>>>(g, F, edge_shift, edge_op, vertex_preprocess_op, vertex_postprocess_op);
         launch_check();
     }
 
@@ -302,8 +313,10 @@ public:
     {
         if (current_traversal_direction != SCATTER) throw "Error in GraphAbstractions::scatter : wrong traversal direction"; // common/advance.hpp:19-26
         if (&_graph != &graph) throw "Error in GraphAbstractionsB200::scatter : API object is attached to another graph";
-        advance_worker(_frontier, false, edge_op, vertex_preprocess_op, vertex_postprocess_op, collective_edge_op,
-                       collective_vertex_preprocess_op, collective_vertex_postprocess_op);
+        // the "collective" triple serves the low-degree region on SX-Aurora; like the reference's GPU backend
+        // (gpu/advance_vect_csr.hpp:56-141) one triple runs everywhere
+        (void)collective_edge_op; (void)collective_vertex_preprocess_op; (void)collective_vertex_postprocess_op;
+        advance_worker(_frontier, false, edge_op, vertex_preprocess_op, vertex_postprocess_op);
     }
     template <typename EdgeOperation>
     void scatter(GraphB200 &_graph, FrontierB200 &_frontier, EdgeOperation &&edge_op)
@@ -322,8 +335,8 @@ public:
     {
         if (current_traversal_direction != GATHER) throw "Error in GraphAbstractions::gather : wrong traversal direction";
         if (&_graph != &graph) throw "Error in GraphAbstractionsB200::gather : API object is attached to another graph";
-        advance_worker(_frontier, true, edge_op, vertex_preprocess_op, vertex_postprocess_op, collective_edge_op,
-                       collective_vertex_preprocess_op, collective_vertex_postprocess_op);
+        (void)collective_edge_op; (void)collective_vertex_preprocess_op; (void)collective_vertex_postprocess_op;
+        advance_worker(_frontier, true, edge_op, vertex_preprocess_op, vertex_postprocess_op);
     }
     template <typename EdgeOperation>
     void gather(GraphB200 &_graph, FrontierB200 &_frontier, EdgeOperation &&edge_op)
@@ -396,7 +409,7 @@ public:
         const int V = _graph.get_vertices_count();
         const long long blocks = ((long long)V + 255) / 256;
         gnf_bitmap_kernel<<<(unsigned)(blocks < max_blocks ? blocks : max_blocks), 256, 0, stream>>>(_graph.info.d_out_ptr, V, filter_bitmap,
-                                                                                              filter_cond);
+                                                                                              (int32_t *)nullptr, filter_cond);
         launch_check();
         check(vglb_gnf_from_bitmap(ctx, _frontier.handle, filter_bitmap));
     }

@@ -30,7 +30,7 @@ _f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
 
 def build(ref: bool = True) -> None:
     """Compile the checkers (make -C oracle). Building the checker is not using it."""
-    targets = ["oracle"] + (["ref"] if ref else [])
+    targets = ["oracle"] + (["ref", "refgpu"] if ref else [])
     subprocess.run(["make", "-s", "-C", _HERE, "-j4"] + targets, check=True)
 
 
@@ -327,3 +327,89 @@ class RefGraph:
         c = np.empty(self.V, np.int32)
         t = self.L.vglref_cc(self.h, c)
         return c, t
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Reference GPU build (-D __USE_GPU__) front-end: the reference's own algorithms on (a) this repo's B200 backend through the
+# include-path overlay ("dropin") or (b) the reference's own CUDA backend recompiled for sm_100a ("refgpu")
+# ---------------------------------------------------------------------------------------------------------------------
+
+def gpu_ref_available(which: str = "dropin") -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", f"libvgl_{which}.so"))
+
+
+_GPU_LIBS = {}
+
+
+def gpu_ref_lib(which: str) -> C.CDLL:
+    if which not in _GPU_LIBS:
+        L = C.CDLL(os.path.join(_HERE, "_ref", f"libvgl_{which}.so"))
+        L.vglgpu_graph_create.argtypes = [C.c_int, C.c_longlong, _i32p, _i32p]
+        L.vglgpu_graph_create.restype = C.c_void_p
+        L.vglgpu_graph_destroy.argtypes = [C.c_void_p]
+        L.vglgpu_bfs.argtypes = [C.c_void_p, C.c_int, _i32p]
+        L.vglgpu_bfs.restype = C.c_double
+        L.vglgpu_pagerank.argtypes = [C.c_void_p, C.c_int, C.c_int, _f32p]
+        L.vglgpu_pagerank.restype = C.c_double
+        L.vglgpu_sssp.argtypes = [C.c_void_p, C.c_ulonglong, C.c_int, _f32p, C.c_int]
+        L.vglgpu_sssp.restype = C.c_double
+        L.vglgpu_cc.argtypes = [C.c_void_p, _i32p]
+        L.vglgpu_cc.restype = C.c_double
+        L.vglgpu_hits.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, C.c_void_p, C.c_void_p]
+        L.vglgpu_hits.restype = C.c_double
+        L.vglgpu_group_mark.argtypes = [C.c_void_p, _i32p, C.c_int, _i32p]
+        L.vglgpu_group_mark.restype = C.c_longlong
+        _GPU_LIBS[which] = L
+    return _GPU_LIBS[which]
+
+
+class GpuRefGraph:
+    """VGL_Graph of the reference's GPU build; `which` = "dropin" (B200 backend through the overlay) or "refgpu"."""
+
+    def __init__(self, V: int, src: np.ndarray, dst: np.ndarray, which: str = "dropin"):
+        self.L = gpu_ref_lib(which)
+        self.which, self.V, self.E = which, V, int(src.shape[0])
+        assert self.L.vglgpu_is_b200_backend() == (1 if which == "dropin" else 0)
+        self.h = self.L.vglgpu_graph_create(V, self.E, np.ascontiguousarray(src, np.int32), np.ascontiguousarray(dst, np.int32))
+        if not self.h:
+            raise RuntimeError("vglgpu_graph_create failed")
+
+    def close(self):
+        if self.h:
+            self.L.vglgpu_graph_destroy(self.h)
+            self.h = None
+
+    def _checked(self, t):
+        if t < 0:
+            raise RuntimeError(f"the reference ({self.which}) threw; see stderr")
+        return t
+
+    def bfs(self, source_orig: int):
+        lv = np.empty(self.V, np.int32)
+        return lv, self._checked(self.L.vglgpu_bfs(self.h, source_orig, lv))
+
+    def pagerank(self, iters: int, push: bool = False):
+        r = np.empty(self.V, np.float32)
+        return r, self._checked(self.L.vglgpu_pagerank(self.h, iters, 1 if push else 0, r))
+
+    def sssp(self, source_orig: int, weight_seed: int, mode: int = 2):
+        d = np.empty(self.V, np.float32)
+        return d, self._checked(self.L.vglgpu_sssp(self.h, weight_seed, source_orig, d, mode))
+
+    def cc(self):
+        c = np.empty(self.V, np.int32)
+        return c, self._checked(self.L.vglgpu_cc(self.h, c))
+
+    def hits(self, steps: int, with_seq: bool = True):
+        a, hb = np.empty(self.V, np.float32), np.empty(self.V, np.float32)
+        sa, sh = np.empty(self.V, np.float32), np.empty(self.V, np.float32)
+        t = self._checked(self.L.vglgpu_hits(self.h, steps, a, hb, sa.ctypes.data if with_seq else None, sh.ctypes.data if with_seq else None))
+        return a, hb, (sa if with_seq else None), (sh if with_seq else None), t
+
+    def group_mark(self, ids_orig):
+        ids = np.ascontiguousarray(ids_orig, np.int32)
+        marks = np.empty(self.V, np.int32)
+        total = self.L.vglgpu_group_mark(self.h, ids, len(ids), marks)
+        if total < 0:
+            raise RuntimeError(f"the reference ({self.which}) threw; see stderr")
+        return marks, int(total)

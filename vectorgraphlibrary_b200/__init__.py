@@ -106,6 +106,9 @@ _SIGNATURES = {
     "vglb_sssp": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.POINTER(Stats)]),
     "vglb_cc": (C.c_int, [_P, _P, _P, C.POINTER(Stats)]),
     "vglb_frontier_create": (C.c_int, [_P, _P, C.POINTER(_P)]),
+    "vglb_frontier_create_borrowed": (C.c_int, [_P, _P, _P, C.POINTER(_P)]),
+    "vglb_frontier_set_ids": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int]),
+    "vglb_graph_borrow_csr": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, C.POINTER(_P)]),
     "vglb_frontier_destroy": (C.c_int, [_P, _P]),
     "vglb_frontier_set_all_active": (C.c_int, [_P, _P]),
     "vglb_frontier_clear": (C.c_int, [_P, _P]),
@@ -545,6 +548,11 @@ class Frontier:
 
     def add_vertex(self, v: int):
         _check(lib().vglb_frontier_add_vertex(self.ctx.h, self.h, v))
+
+    def add_group_of_vertices(self, ids):
+        """FrontierVectorCSR::add_group_of_vertices: the reference sorts the list ascending first; so does this mirror."""
+        ids = np.ascontiguousarray(np.sort(np.asarray(ids, np.int32)))
+        _check(lib().vglb_frontier_set_ids(self.ctx.h, self.h, ids.ctypes.data, len(ids), 0))
 
     def info(self) -> FrontierInfo:
         fi = FrontierInfo()

@@ -276,11 +276,18 @@ extern "C" int vglb_cc(vglb_ctx *ctx, vglb_graph *g, int32_t *d_labels, vglb_sta
     view.adj = g->d_out_adj;
     view.V = V;
     for (int t = 0; t < VGLB_NUM_TIERS; t++) view.tier_border[t] = g->tier_border[t];
-    const vglb::AllActivePlan plan = vglb::plan_all_active(view);
+    view.max_degree = g->max_degree;
+    const bool generic = getenv("VGLB_CC_GENERIC") != NULL;
+    int64_t hub_edges = 0; // edges of the rows with >= 4096 edges = row pointer at the first tier border
+    if (generic && g->tier_border[0] > 0)
+    {
+        CUDA_TRY(cudaMemcpyAsync(&hub_edges, g->d_out_ptr + g->tier_border[0], 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    const vglb::AllActivePlan plan = vglb::plan_all_active<vglb::NoVertexOp, vglb::NoVertexOp>(view, g->E, hub_edges);
     VGLB_REQUIRE(plan.blocks < 0x7fffffffLL, "vglb_cc: grid too large");
     CcHookOp hook{d_labels, d_changed};
     vglb::NoVertexOp none;
-    const bool generic = getenv("VGLB_CC_GENERIC") != NULL;
 
     CUDA_TRY(cudaEventRecord(ctx->ev_start, st));
     cc_init_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_labels, V);
@@ -294,7 +301,7 @@ extern "C" int vglb_cc(vglb_ctx *ctx, vglb_graph *g, int32_t *d_labels, vglb_sta
         {
             if (plan.blocks > 0)
             {
-                vglb::advance_all_active_kernel<<<(unsigned)plan.blocks, vglb::kAdvThreads, 0, st>>>(view, plan, 0LL, hook, none, none, hook, none, none);
+                vglb::advance_all_active_kernel<<<(unsigned)plan.blocks, vglb::kAdvThreads, 0, st>>>(view, plan, 0LL, hook, none, none);
                 KERNEL_TRY();
                 ctx->launches++;
             }

@@ -115,6 +115,7 @@ struct vglb_graph
     void *d_part_lists;         // SSSP: per-owner lists of (column, distance) updates this rank produced in a round
     uint32_t *d_vec_peer[8];    // the peers' d_part_lists, CUDA IPC mappings (own entry = own buffer)
     int vec_peers_mapped;       // 0 = not tried, 1 = mapped, -1 = mapping failed (dense allreduce exchange is used)
+    int borrowed_csr;           // d_out_ptr / d_out_adj belong to the caller (vglb_graph_borrow_csr): never freed here
     int ipc_exported;           // buffers of this graph were offered to the peers over CUDA IPC: vglb_graph_free is a collective
     // BFS / SSSP / CC scratch
     uint32_t *d_visited, *d_front_bm[2];
@@ -141,6 +142,7 @@ struct vglb_frontier
     int64_t neighbours;
     int32_t tier_size[3];
     int32_t *d_ids;
+    int borrowed_ids;      // d_ids belongs to the caller (vglb_frontier_create_borrowed)
     uint32_t *d_bitmap;
     void *d_tile_status;   // [8 counters][one look-back status word per GNF tile]
     int64_t tiles;

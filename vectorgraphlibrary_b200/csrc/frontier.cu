@@ -172,6 +172,13 @@ __global__ void frontier_fill_bitmap_kernel(uint32_t *bitmap, int32_t V)
 
 extern "C" int vglb_frontier_create(vglb_ctx *ctx, vglb_graph *g, vglb_frontier **out)
 {
+    return vglb_frontier_create_borrowed(ctx, g, NULL, out);
+}
+
+// `d_ids` != NULL: the id list lives in the caller's array of at least `vertices` ints (the reference frontier's own ids[],
+// base_frontier.h:18 — the compaction then writes straight into the object the algorithm holds)
+extern "C" int vglb_frontier_create_borrowed(vglb_ctx *ctx, vglb_graph *g, int32_t *d_ids, vglb_frontier **out)
+{
     VGLB_REQUIRE(ctx != NULL && g != NULL && out != NULL, "vglb_frontier_create: NULL argument");
     CUDA_TRY(cudaSetDevice(ctx->device));
     vglb_frontier *f = (vglb_frontier *)calloc(1, sizeof(vglb_frontier));
@@ -180,12 +187,17 @@ extern "C" int vglb_frontier_create(vglb_ctx *ctx, vglb_graph *g, vglb_frontier 
     const size_t words = ((size_t)g->V + 31) / 32 + 32;
     const size_t tiles = ((size_t)g->V + GNF_TILE - 1) / GNF_TILE + 1;
     cudaError_t e = vglb_dev_alloc(&f->d_bitmap, words * 4);
-    if (e == cudaSuccess) e = vglb_dev_alloc(&f->d_ids, ((size_t)g->V + 32) * 4);
+    if (d_ids)
+    {
+        f->d_ids = d_ids;
+        f->borrowed_ids = 1;
+    }
+    else if (e == cudaSuccess) e = vglb_dev_alloc(&f->d_ids, ((size_t)g->V + 32) * 4);
     if (e == cudaSuccess) e = vglb_dev_alloc(&f->d_tile_status, (tiles + G_COUNT) * 8);
     if (e != cudaSuccess)
     {
         cudaGetLastError();
-        vglb_dev_free(f->d_bitmap); vglb_dev_free(f->d_ids); vglb_dev_free(f->d_tile_status);
+        vglb_dev_free(f->d_bitmap); if (!f->borrowed_ids) vglb_dev_free(f->d_ids); vglb_dev_free(f->d_tile_status);
         free(f);
         vglb_set_error("vglb_frontier_create: cudaMalloc failed: %s", cudaGetErrorString(e));
         return VGLB_ENOMEM;
@@ -202,7 +214,7 @@ extern "C" int vglb_frontier_destroy(vglb_ctx *ctx, vglb_frontier *f)
     VGLB_REQUIRE(ctx != NULL, "vglb_frontier_destroy: ctx is NULL");
     if (!f) return VGLB_OK;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    vglb_dev_free(f->d_bitmap); vglb_dev_free(f->d_ids); vglb_dev_free(f->d_tile_status);
+    vglb_dev_free(f->d_bitmap); if (!f->borrowed_ids) vglb_dev_free(f->d_ids); vglb_dev_free(f->d_tile_status);
     free(f);
     return VGLB_OK;
 }
@@ -264,6 +276,82 @@ extern "C" int vglb_frontier_add_vertex(vglb_ctx *ctx, vglb_frontier *f, int32_t
     const int tier = v < g->tier_border[0] ? 0 : (v < g->tier_border[1] ? 1 : 2);
     f->tier_size[0] = f->tier_size[1] = f->tier_size[2] = 0;
     f->tier_size[tier] = 1;
+    return VGLB_OK;
+}
+
+// FrontierVectorCSR::add_group_of_vertices (modification.hpp:88-145): an explicit id list becomes the frontier. The reference
+// sorts the list ascending first (Sorter::sort) — which is what makes the degree tiers contiguous prefixes; here the list must
+// arrive ascending and duplicate-free (checked on the device). Only on an empty frontier, like the reference.
+__global__ void frontier_set_ids_kernel(const int32_t *__restrict__ ids, int32_t n, int32_t V, const int64_t *__restrict__ ptr, int32_t b0,
+                                        int32_t b1, uint32_t *__restrict__ bitmap, unsigned long long *__restrict__ counters)
+{
+    long long deg = 0;
+    int t0 = 0, t1 = 0, bad = 0;
+    for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const int32_t v = ids[i];
+        if (v < 0 || v >= V || (i > 0 && ids[i - 1] >= v))
+        {
+            bad = 1;
+            continue;
+        }
+        atomicOr(&bitmap[v >> 5], 1u << (v & 31));
+        deg += ptr[v + 1] - ptr[v];
+        t0 += v < b0;
+        t1 += v >= b0 && v < b1;
+    }
+    deg = warp_sum_i64(deg);
+    t0 = (int)warp_sum_i64(t0);
+    t1 = (int)warp_sum_i64(t1);
+    bad = __any_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0)
+    {
+        if (deg) atomicAdd(&counters[G_NEIGHBOURS], (unsigned long long)deg);
+        if (t0) atomicAdd(&counters[G_TIER0], (unsigned long long)t0);
+        if (t1) atomicAdd(&counters[G_TIER1], (unsigned long long)t1);
+        if (bad) atomicAdd(&counters[G_TICKET], 1ULL);
+    }
+}
+
+extern "C" int vglb_frontier_set_ids(vglb_ctx *ctx, vglb_frontier *f, const int32_t *ids, int32_t n, int ids_on_device)
+{
+    VGLB_REQUIRE(ctx != NULL && f != NULL && (n == 0 || ids != NULL), "vglb_frontier_set_ids: NULL argument");
+    VGLB_REQUIRE(n >= 0 && n <= f->g->V, "vglb_frontier_set_ids: more ids than vertices");
+    if (f->size > 0)
+    {
+        vglb_set_error("VGL ERROR: can not add vertices to non-empty frontier"); // modification.hpp:90-93
+        return VGLB_EINVAL;
+    }
+    const vglb_graph *g = f->g;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (n > 0 && ids != f->d_ids)
+        CUDA_TRY(cudaMemcpyAsync(f->d_ids, ids, (size_t)n * 4, ids_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    unsigned long long *counters = (unsigned long long *)f->d_tile_status;
+    CUDA_TRY(cudaMemsetAsync(counters, 0, G_COUNT * 8, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(f->d_bitmap, 0, (((size_t)g->V + 31) / 32) * 4, ctx->stream));
+    if (n > 0)
+    {
+        const int blocks = (int)(ceil_div64(n, 256) < ctx->sm_count * 8 ? ceil_div64(n, 256) : ctx->sm_count * 8);
+        frontier_set_ids_kernel<<<blocks, 256, 0, ctx->stream>>>(f->d_ids, n, g->V, g->d_out_ptr, g->tier_border[0], g->tier_border[1],
+                                                                f->d_bitmap, counters);
+        KERNEL_TRY();
+        ctx->launches++;
+    }
+    unsigned long long *h = (unsigned long long *)ctx->h_counters;
+    CUDA_TRY(cudaMemcpyAsync(h, counters, G_COUNT * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (h[G_TICKET])
+    {
+        CUDA_TRY(cudaMemsetAsync(f->d_bitmap, 0, (((size_t)g->V + 31) / 32) * 4, ctx->stream));
+        vglb_set_error("vglb_frontier_set_ids: ids must be ascending, distinct and in [0, V)");
+        return VGLB_EINVAL;
+    }
+    f->size = n;
+    f->neighbours = (int64_t)h[G_NEIGHBOURS];
+    f->tier_size[0] = (int32_t)h[G_TIER0];
+    f->tier_size[1] = (int32_t)h[G_TIER1];
+    f->tier_size[2] = n - f->tier_size[0] - f->tier_size[1];
+    f->sparsity_type = n == g->V ? VGLB_FRONTIER_ALL_ACTIVE : VGLB_FRONTIER_SPARSE;
     return VGLB_OK;
 }
 

@@ -253,7 +253,12 @@ void vglb_graph_free_fields(vglb_graph *g)
     graph_close_peer_mappings(g); // importers close before any exporter frees (vglb_graph_free orders the ranks)
     vglb_dev_free(g->d_part_bm[0]); vglb_dev_free(g->d_part_bm[1]); vglb_dev_free(g->d_part_bm[2]); vglb_dev_free(g->d_part_stage);
     vglb_dev_free(g->d_part_vec); vglb_dev_free(g->d_part_prev); vglb_dev_free(g->d_part_lists);
-    vglb_dev_free(g->d_out_ptr); vglb_dev_free(g->d_out_adj); vglb_dev_free(g->d_in_ptr); vglb_dev_free(g->d_in_adj);
+    if (!g->borrowed_csr)
+    {
+        vglb_dev_free(g->d_out_ptr);
+        vglb_dev_free(g->d_out_adj);
+    }
+    vglb_dev_free(g->d_in_ptr); vglb_dev_free(g->d_in_adj);
     vglb_dev_free(g->d_fwd); vglb_dev_free(g->d_bwd); vglb_dev_free(g->d_edge_order);
     vglb_dev_free(g->d_indeg_noloops); vglb_dev_free(g->d_pr_inv); vglb_dev_free(g->d_pr_contrib[0]); vglb_dev_free(g->d_pr_contrib[1]); vglb_dev_free(g->d_pr_dangling); vglb_dev_free(g->d_pr_tasks); vglb_dev_free(g->d_pr_piece_partial); vglb_dev_free(g->d_pr_piece_count); vglb_dev_free(g->d_pr_ve_adj); vglb_dev_free(g->d_pr_ve_ptr);
     vglb_dev_free(g->d_visited); vglb_dev_free(g->d_front_bm[0]); vglb_dev_free(g->d_front_bm[1]);
@@ -615,6 +620,33 @@ extern "C" int vglb_graph_from_csr(vglb_ctx *ctx, int32_t V, int64_t E, const in
         return VGLB_EINVAL;
     }
     BUILD_TRY(vglb_graph_compute_tiers(ctx, g));
+    vglb_graph_set_unpartitioned(g);
+    *out_graph = g;
+    return VGLB_OK;
+}
+
+// One direction of a VectorCSRGraph that already lives in device-accessible memory (cudaMalloc'ed or managed: the reference's
+// GPU build keeps vertex_pointers / adjacent_ids in cudaMallocManaged memory, memory_API.hpp:3-15): nothing is copied, the
+// arrays stay the caller's. What the borrowed graph adds is what the operators need on top of the arrays: the degree-tier
+// borders (estimate_thresholds, vect_csr/nec_api.hpp:5-50) and a home for frontier objects.
+extern "C" int vglb_graph_borrow_csr(vglb_ctx *ctx, int32_t V, int64_t E, const int64_t *d_ptr, const int32_t *d_adj, vglb_graph **out_graph)
+{
+    VGLB_REQUIRE(ctx != NULL && out_graph != NULL && d_ptr != NULL, "vglb_graph_borrow_csr: NULL argument");
+    VGLB_REQUIRE(V > 0 && E >= 0 && (E == 0 || d_adj != NULL), "vglb_graph_borrow_csr: bad sizes");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    vglb_graph *g = (vglb_graph *)calloc(1, sizeof(vglb_graph));
+    if (!g) return VGLB_ENOMEM;
+    g->V = V;
+    g->E = E;
+    g->borrowed_csr = 1;
+    g->d_out_ptr = const_cast<int64_t *>(d_ptr);
+    g->d_out_adj = const_cast<int32_t *>(d_adj);
+    int rc = vglb_graph_compute_tiers(ctx, g); // also rejects rows that are not degree-sorted (VGLB_EUNSORTED)
+    if (rc != VGLB_OK)
+    {
+        free(g);
+        return rc;
+    }
     vglb_graph_set_unpartitioned(g);
     *out_graph = g;
     return VGLB_OK;
