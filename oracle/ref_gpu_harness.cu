@@ -154,8 +154,11 @@ double vglgpu_pagerank(void *h, int iters, int traversal, float *ranks_orig)
 }
 
 /* ShortestPaths::vgl_dijkstra; mode 0 = ALL_ACTIVE PUSH, 1 = ALL_ACTIVE PULL, 2 = PARTIAL_ACTIVE (push).
- * Weights: vglb_edge_weight(orig_src, orig_dst, seed) on the outgoing CSR, mirrored to the incoming direction the way
- * EdgesArray::set_all_random does (vect_csr_edges_array.hpp:49-65). */
+ * Weights: vglb_edge_weight(orig_src, orig_dst, seed) for every position of the outgoing AND the incoming CSR (the weight is a
+ * function of the edge's end points, so both directions are filled from the hash). The reference would mirror out -> in with
+ * VGL_Graph::copy_outgoing_to_incoming_edges, but under __USE_GPU__ that call moves BYTES, not elements
+ * (vect_csr/reorder.hpp:72-74 passes the char* casts to the templated cuda_reorder_gather_copy) — a defect of the reference's GPU
+ * build that is independent of the backend, so the harness does not go through it. */
 double vglgpu_sssp(void *h, unsigned long long weight_seed, int source_orig, float *dist_orig, int mode)
 {
     GpuRefGraph *rg = (GpuRefGraph *)h;
@@ -181,7 +184,13 @@ double vglgpu_sssp(void *h, unsigned long long weight_seed, int source_orig, flo
         float *w_in = w_out_ve + out->get_edges_count_in_ve();
         float *w_in_ve = w_in + E;
         out->get_ve_ptr()->copy_array_from_csr_to_ve(w_out_ve, w);
-        g.copy_outgoing_to_incoming_edges(w, w_in);
+        const long long *iptr = in->get_vertex_pointers();
+        const int *iadj = in->get_adjacent_ids();
+        for (int v = 0; v < rg->vertices; v++) /* row v of the incoming CSR (GATHER numbering) lists the sources of edges u -> v */
+        {
+            int ov = g.reorder(v, GATHER, ORIGINAL);
+            for (long long p = iptr[v]; p < iptr[v + 1]; p++) w_in[p] = vglb_edge_weight(g.reorder(iadj[p], GATHER, ORIGINAL), ov, weight_seed);
+        }
         in->get_ve_ptr()->copy_array_from_csr_to_ve(w_in_ve, w_in);
 
         VerticesArray<float> dist(g, SCATTER);
