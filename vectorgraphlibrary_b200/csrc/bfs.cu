@@ -111,7 +111,7 @@ template <int NT, int MODE>
 __device__ __forceinline__ void td_expand(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, int64_t s, int64_t e, int tid,
                                           uint32_t *__restrict__ visited, int32_t *__restrict__ levels, int32_t next_level,
                                           int32_t b0, int32_t b1, const TierQueues &nq, unsigned long long *counters, long long &mf,
-                                          const PartArgs &A)
+                                          const PartArgs &A, int &found)
 {
     for (int64_t p0 = s + tid;; p0 += NT * BFS_TD_UNROLL)
     {
@@ -145,7 +145,7 @@ __device__ __forceinline__ void td_expand(const int64_t *__restrict__ ptr, const
                 won[k] = !(old & bit);
             }
         }
-        if (MODE == 0)
+        if (MODE == 0 || MODE == 3)
         {
 #pragma unroll
             for (int k = 0; k < BFS_TD_UNROLL; k++)
@@ -153,8 +153,17 @@ __device__ __forceinline__ void td_expand(const int64_t *__restrict__ ptr, const
                 {
                     levels[v[k]] = next_level;
                     mf += ptr[v[k] + 1] - ptr[v[k]]; // out-degree of the new frontier (m_f of the direction heuristic)
+                    if (MODE == 3)
+                    {
+                        // a level that discovers millions of vertices: the next frontier is emitted as a BITMAP (scattered
+                        // atomicOr) instead of through the three queue counters, whose same-address atomics serialise
+                        // (0.78 ms for an 18 M-edge / 4.8 M-discovery level); the next level is bottom-up more often than not
+                        uint32_t *next_bm = reinterpret_cast<uint32_t *>(A.lists);
+                        atomicOr(&next_bm[v[k] >> 5], 1u << (v[k] & 31));
+                        found++;
+                    }
                 }
-            enqueue_binned_multi(won, v, b0, b1, nq, counters);
+            if (MODE == 0) enqueue_binned_multi(won, v, b0, b1, nq, counters);
         }
         if (MODE == 2)
         {
@@ -179,7 +188,7 @@ __device__ __forceinline__ void td_expand(const int64_t *__restrict__ ptr, const
 
 template <int MODE>
 __global__ void __launch_bounds__(BFS_THREADS)
-bfs_td_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, TierQueues cq, int32_t n_big, int32_t big_chunks,
+bfs_td_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, TierQueues cq, int32_t n_big, int32_t hub_ctas,
               int32_t n_mid, int32_t n_small, int32_t blocks_mid, int32_t blocks_small, uint32_t *__restrict__ visited,
               int32_t *__restrict__ levels, int32_t next_level, int32_t b0, int32_t b1, TierQueues nq,
               unsigned long long *counters, PartArgs A)
@@ -187,14 +196,40 @@ bfs_td_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, 
     const int b = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     long long edges = 0, mf = 0;
-    // hubs: one CTA per BFS_BIG_CHUNK edges of the row (the largest rows of a scale-26 Kronecker graph have > 10^6 edges)
-    const int big_blocks = n_big * big_chunks;
+    int found = 0;
+    // hubs (>= 4096 edges; the largest rows of a scale-26 Kronecker graph have > 10^6): `hub_ctas` CTAs share every hub row
+    // of the frontier, BFS_BIG_CHUNK edges at a time — chunk j of the i-th queued hub goes to CTA (j + 7 i) mod hub_ctas.
+    // (One CTA per (row, chunk slot of the LONGEST row) launched hundreds of thousands of empty CTAs when a few thousand
+    // mid-sized hubs were queued: 0.78 ms for an 18 M-edge level.) Row ranges are staged through shared memory 256 at a time.
+    const int big_blocks = hub_ctas;
     if (b < big_blocks)
     {
-        const int32_t u = cq.q[0][b / big_chunks];
-        const int64_t s = ptr[u] + (int64_t)(b % big_chunks) * BFS_BIG_CHUNK, e = min(ptr[u + 1], s + BFS_BIG_CHUNK);
-        if (threadIdx.x == 0) edges = max(e - s, (int64_t)0);
-        td_expand<BFS_THREADS, MODE>(ptr, adj, s, e, threadIdx.x, visited, levels, next_level, b0, b1, nq, counters, mf, A);
+        __shared__ int64_t s_row_start[BFS_THREADS], s_row_end[BFS_THREADS];
+        for (int base = 0; base < n_big; base += BFS_THREADS)
+        {
+            __syncthreads();
+            if (base + (int)threadIdx.x < n_big)
+            {
+                const int32_t u = cq.q[0][base + threadIdx.x];
+                s_row_start[threadIdx.x] = ptr[u];
+                s_row_end[threadIdx.x] = ptr[u + 1];
+            }
+            __syncthreads();
+            const int cnt = min(BFS_THREADS, n_big - base);
+            for (int k = 0; k < cnt; k++)
+            {
+                const int64_t rs = s_row_start[k], re = s_row_end[k];
+                const int nchunks = (int)((re - rs + BFS_BIG_CHUNK - 1) / BFS_BIG_CHUNK);
+                int first = (b - (int)(((long long)(base + k) * 7) % hub_ctas)) % hub_ctas;
+                if (first < 0) first += hub_ctas;
+                for (int j = first; j < nchunks; j += hub_ctas)
+                {
+                    const int64_t s = rs + (int64_t)j * BFS_BIG_CHUNK, e = min(re, s + BFS_BIG_CHUNK);
+                    if (threadIdx.x == 0) edges += e - s;
+                    td_expand<BFS_THREADS, MODE>(ptr, adj, s, e, threadIdx.x, visited, levels, next_level, b0, b1, nq, counters, mf, A, found);
+                }
+            }
+        }
     }
     else if (b < big_blocks + blocks_mid)
     {
@@ -204,7 +239,7 @@ bfs_td_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, 
             const int32_t u = cq.q[1][i];
             const int64_t s = ptr[u], e = ptr[u + 1];
             if (lane == 0) edges += e - s;
-            td_expand<32, MODE>(ptr, adj, s, e, lane, visited, levels, next_level, b0, b1, nq, counters, mf, A);
+            td_expand<32, MODE>(ptr, adj, s, e, lane, visited, levels, next_level, b0, b1, nq, counters, mf, A, found);
         }
     }
     else
@@ -226,13 +261,18 @@ bfs_td_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, 
                 e = ptr[u + 1];
                 if (gl == 0) edges += e - s;
             }
-            td_expand<G, MODE>(ptr, adj, s, e, gl, visited, levels, next_level, b0, b1, nq, counters, mf, A);
+            td_expand<G, MODE>(ptr, adj, s, e, gl, visited, levels, next_level, b0, b1, nq, counters, mf, A, found);
         }
     }
     edges = warp_sum_i64(edges);
     mf = warp_sum_i64(mf);
     if (lane == 0 && edges) atomicAdd(&counters[C_EDGES], (unsigned long long)edges);
     if (lane == 0 && mf) atomicAdd(&counters[C_MF], (unsigned long long)mf);
+    if (MODE == 3)
+    {
+        found = (int)warp_sum_i64(found);
+        if (lane == 0 && found) atomicAdd(&counters[C_FOUND], (unsigned long long)found);
+    }
 }
 
 // owner side of a partitioned top-down level: the peers' lists of columns they discovered in this rank's slice, read out
@@ -280,6 +320,7 @@ bfs_apply_lists_kernel(const unsigned long long *const *__restrict__ peer_lists,
 // (the four ids and then the four frontier bits are independent loads), then warp-cooperative scans of the long rows
 // with ballot early exit. Bitmap words are written without atomics; in-rows list sources hubs-first.
 #define BFS_BU_WORDS 4
+#define BFS_BU_LONG_UNROLL 8
 #ifndef BFS_BU_MIN_CTAS
 #define BFS_BU_MIN_CTAS 4 // A/B on Kronecker s26: 4 CTAs/SM (60 registers) 1.48-2.02 ms, 5 (48 regs) +3 %, 6 (40 regs, spills) +20 %
 #endif
@@ -385,15 +426,25 @@ bfs_bu_kernel(const int64_t *__restrict__ in_ptr, const int32_t *__restrict__ in
                     const int64_t ps = __shfl_sync(FULL, s[t], src_lane) + BFS_BU_PROBE_MAX;
                     const int64_t pend = __shfl_sync(FULL, e[t], src_lane);
                     bool hit = false;
-                    for (int64_t p0 = ps; p0 < pend; p0 += 32)
+                    // BFS_BU_LONG_UNROLL x 32 neighbours per round trip: a vertex without a parent in the frontier (most of them in the
+                    // first bottom-up level) scans its whole in-row, and 32 edges per dependent load pair was the kernel's bottleneck
+                    for (int64_t p0 = ps; p0 < pend; p0 += 32 * BFS_BU_LONG_UNROLL)
                     {
-                        const int64_t p = p0 + lane;
-                        bool h = false;
-                        if (p < pend)
+                        int32_t y[BFS_BU_LONG_UNROLL];
+#pragma unroll
+                        for (int k = 0; k < BFS_BU_LONG_UNROLL; k++)
                         {
-                            edges++;
-                            h = bm_test(cur_bm, in_adj[p]);
+                            const int64_t p = p0 + k * 32 + lane;
+                            y[k] = p < pend ? in_adj[p] : -1;
                         }
+                        bool h = false;
+#pragma unroll
+                        for (int k = 0; k < BFS_BU_LONG_UNROLL; k++)
+                            if (y[k] >= 0)
+                            {
+                                edges++;
+                                h |= bm_test(cur_bm, y[k]);
+                            }
                         if (__any_sync(FULL, h))
                         {
                             hit = true;
@@ -664,10 +715,11 @@ static int bfs_partitioned_bitmaps(vglb_ctx *ctx, vglb_graph *g, int32_t source,
             CUDA_TRY(cudaMemsetAsync(next_bm, 0, (size_t)words * 4, st)); // candidates
             const int blocks_mid = (int)min((int64_t)max_blocks, ceil_div64(n[1], BFS_THREADS / 32));
             const int blocks_small = (int)min((int64_t)max_blocks, ceil_div64(n[2], BFS_THREADS / BFS_SMALL_LANES));
-            const int64_t grid = (int64_t)n[0] * big_chunks + blocks_mid + blocks_small;
+            const int hub_ctas = (int)min((int64_t)n[0] * big_chunks, (int64_t)ctx->sm_count * 4); // CTAs that share the queued hub rows
+            const int64_t grid = (int64_t)hub_ctas + blocks_mid + blocks_small;
             if (grid > 0)
             {
-                bfs_td_kernel<1><<<(unsigned)grid, BFS_THREADS, 0, st>>>(g->d_out_ptr, g->d_out_adj, cq, n[0], big_chunks, n[1], n[2], blocks_mid,
+                bfs_td_kernel<1><<<(unsigned)grid, BFS_THREADS, 0, st>>>(g->d_out_ptr, g->d_out_adj, cq, n[0], hub_ctas, n[1], n[2], blocks_mid,
                                                                        blocks_small, visited, (int32_t *)next_bm, level + 1, b0, b1,
                                                                        cq, d_cnt, PartArgs());
                 KERNEL_TRY();
@@ -868,10 +920,11 @@ static int bfs_partitioned(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t
             CUDA_TRY(cudaMemsetAsync(A.lists, 0, (size_t)P * 8, st)); // list lengths (the peers finished reading them: see below)
             const int blocks_mid = (int)min((int64_t)max_blocks, ceil_div64(n[1], BFS_THREADS / 32));
             const int blocks_small = (int)min((int64_t)max_blocks, ceil_div64(n[2], BFS_THREADS / BFS_SMALL_LANES));
-            const int64_t grid = (int64_t)n[0] * big_chunks + blocks_mid + blocks_small;
+            const int hub_ctas = (int)min((int64_t)n[0] * big_chunks, (int64_t)ctx->sm_count * 4); // CTAs that share the queued hub rows
+            const int64_t grid = (int64_t)hub_ctas + blocks_mid + blocks_small;
             if (grid > 0)
             {
-                bfs_td_kernel<2><<<(unsigned)grid, BFS_THREADS, 0, st>>>(g->d_out_ptr, g->d_out_adj, cq, n[0], big_chunks, n[1], n[2], blocks_mid,
+                bfs_td_kernel<2><<<(unsigned)grid, BFS_THREADS, 0, st>>>(g->d_out_ptr, g->d_out_adj, cq, n[0], hub_ctas, n[1], n[2], blocks_mid,
                                                                        blocks_small, visited, d_levels, level + 1, b0, b1, nq, d_cnt, A);
                 KERNEL_TRY();
                 ctx->launches++;
@@ -1081,16 +1134,32 @@ extern "C" int vglb_bfs(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t *d
         trace_t = trace_now();
     }
 
+    long long m_f_cur = 0; // out-edges of the current frontier (accumulated by the level that produced it; unknown for the source)
+    const long long bitmap_out_edges = getenv("VGLB_BFS_NO_BITMAP_OUT") ? (1LL << 62) : (1LL << 20); // developer knob
     while (n_cur > 0)
     {
+        // a top-down level that is about to inspect more than a million edges emits its discoveries as a bitmap
+        const bool bitmap_out = !bottom_up && m_f_cur > bitmap_out_edges;
         if (!bottom_up)
         {
             const int blocks_mid = (int)min((int64_t)max_blocks, ceil_div64(n[1], BFS_THREADS / 32));
             const int blocks_small = (int)min((int64_t)max_blocks, ceil_div64(n[2], BFS_THREADS / BFS_SMALL_LANES));
-            const int64_t grid = (int64_t)n[0] * big_chunks + blocks_mid + blocks_small;
-            bfs_td_kernel<0><<<(unsigned)grid, BFS_THREADS, 0, st>>>(g->d_out_ptr, g->d_out_adj, cq, n[0], big_chunks, n[1], n[2], blocks_mid,
-                                                                   blocks_small, g->d_visited, d_levels, level + 1, b0, b1, nq, d_cnt,
-                                                                   PartArgs());
+            const int hub_ctas = (int)min((int64_t)n[0] * big_chunks, (int64_t)ctx->sm_count * 4); // CTAs that share the queued hub rows
+            const int64_t grid = (int64_t)hub_ctas + blocks_mid + blocks_small;
+            if (bitmap_out)
+            {
+                PartArgs out;
+                memset(&out, 0, sizeof(out));
+                out.lists = reinterpret_cast<unsigned long long *>(next_bm);
+                CUDA_TRY(cudaMemsetAsync(next_bm, 0, words * 4, st));
+                bfs_td_kernel<3><<<(unsigned)grid, BFS_THREADS, 0, st>>>(g->d_out_ptr, g->d_out_adj, cq, n[0], hub_ctas, n[1], n[2], blocks_mid,
+                                                                       blocks_small, g->d_visited, d_levels, level + 1, b0, b1, nq, d_cnt, out);
+                tot_frontier_bytes += (int64_t)words * 4;
+            }
+            else
+                bfs_td_kernel<0><<<(unsigned)grid, BFS_THREADS, 0, st>>>(g->d_out_ptr, g->d_out_adj, cq, n[0], hub_ctas, n[1], n[2], blocks_mid,
+                                                                       blocks_small, g->d_visited, d_levels, level + 1, b0, b1, nq, d_cnt,
+                                                                       PartArgs());
             KERNEL_TRY();
             ctx->launches++;
             tot_rows += n_cur;
@@ -1104,21 +1173,23 @@ extern "C" int vglb_bfs(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t *d
             bu_levels++;
             tot_frontier_bytes += (int64_t)words * 4 * 3; // visited read, frontier read, next written
         }
-        CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, C_COUNT * 8, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
+        rc = vglb_counters_fetch(ctx, d_cnt, C_COUNT);
+        if (rc != VGLB_OK) return rc;
         levels_run++;
         int32_t nn[3] = {(int32_t)h_cnt[C_NEXT_BIG], (int32_t)h_cnt[C_NEXT_MID], (int32_t)h_cnt[C_NEXT_SMALL]};
-        const long long n_next = bottom_up ? (long long)h_cnt[C_FOUND] : (long long)nn[0] + nn[1] + nn[2];
+        const bool out_is_bitmap = bottom_up || bitmap_out; // the next frontier sits in next_bm (else in the queues nq)
+        const long long n_next = out_is_bitmap ? (long long)h_cnt[C_FOUND] : (long long)nn[0] + nn[1] + nn[2];
         const long long in_lvl = (long long)h_cnt[C_EDGES];
+        const long long m_f_next = (long long)h_cnt[C_MF]; // accumulated by the top-down advance itself (0 after a bottom-up level)
         tot_edges += in_lvl;
         if (bottom_up) tot_rows += (long long)h_cnt[C_ROWS];
-        else tot_frontier_bytes += 8 * n_next; // queue written now, read next level
+        else if (!bitmap_out) tot_frontier_bytes += 8 * n_next; // queue written now, read next level
         visited_total += n_next;
         if (trace)
         {
             const double now = trace_now();
-            fprintf(stderr, "bfs level %d (%s): frontier %lld, inspected %lld edges, found %lld, %.1f us since the previous line\n", level,
-                    bottom_up ? "bottom-up" : "top-down", n_cur, in_lvl, n_next, (now - trace_t) * 1e6);
+            fprintf(stderr, "bfs level %d (%s%s): frontier %lld, inspected %lld edges, found %lld, %.1f us since the previous line\n", level,
+                    bottom_up ? "bottom-up" : "top-down", bitmap_out ? ", bitmap out" : "", n_cur, in_lvl, n_next, (now - trace_t) * 1e6);
             trace_t = now;
         }
         if (n_next == 0) break;
@@ -1131,8 +1202,7 @@ extern "C" int vglb_bfs(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t *d
             const long long unvisited = (long long)V - visited_total;
             if (!bottom_up && n_cur < n_next)
             {
-                const long long m_f = (long long)h_cnt[C_MF]; // accumulated by the advance itself
-                if (m_f >= (unvisited * factor + V) / alpha) next_bu = true;
+                if (m_f_next >= (unvisited * factor + V) / alpha) next_bu = true;
             }
             else if (bottom_up && n_cur >= n_next)
             {
@@ -1140,12 +1210,12 @@ extern "C" int vglb_bfs(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t *d
             }
         }
         CUDA_TRY(cudaMemsetAsync(d_cnt, 0, C_COUNT * 8, st));
-        if (!bottom_up && !next_bu)
+        if (!out_is_bitmap && !next_bu)
         {
             TierQueues t = cq; cq = nq; nq = t;
             n[0] = nn[0]; n[1] = nn[1]; n[2] = nn[2];
         }
-        else if (!bottom_up && next_bu)
+        else if (!out_is_bitmap && next_bu)
         {
             CUDA_TRY(cudaMemsetAsync(cur_bm, 0, words * 4, st));
             bfs_queue_to_bitmap_kernel<<<(unsigned)min((int64_t)max_blocks, ceil_div64(n_next, 256)), 256, 0, st>>>(
@@ -1154,7 +1224,7 @@ extern "C" int vglb_bfs(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t *d
             ctx->launches++;
             tot_frontier_bytes += (int64_t)words * 4 + 4 * n_next;
         }
-        else if (bottom_up && next_bu)
+        else if (out_is_bitmap && next_bu)
         {
             uint32_t *t = cur_bm; cur_bm = next_bm; next_bm = t;
         }
@@ -1164,12 +1234,15 @@ extern "C" int vglb_bfs(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t *d
                 next_bm, V, b0, b1, cq, d_cnt);
             KERNEL_TRY();
             ctx->launches++;
-            CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, 3 * 8, cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
+            rc = vglb_counters_fetch(ctx, d_cnt, 3);
+            if (rc != VGLB_OK) return rc;
             n[0] = (int32_t)h_cnt[0]; n[1] = (int32_t)h_cnt[1]; n[2] = (int32_t)h_cnt[2];
             CUDA_TRY(cudaMemsetAsync(d_cnt, 0, C_COUNT * 8, st));
             tot_frontier_bytes += (int64_t)words * 4 + 4 * n_next;
         }
+        // m_f of the frontier the next top-down level expands: known after a top-down level; after a bottom-up level the
+        // frontier that goes back to top-down is small (that is why the heuristic switched)
+        m_f_cur = bottom_up ? 0 : m_f_next;
         bottom_up = next_bu;
         n_cur = n_next;
         level++;

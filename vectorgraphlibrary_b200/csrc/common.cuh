@@ -64,6 +64,11 @@ struct vglb_ctx
     void *d_flush;         // L2 flush buffer
     size_t flush_bytes;
     int64_t launches;      // kernels launched since the last reset (gpu_launches evidence)
+    // counter mailbox: pinned host memory mapped into the device; a 1-warp kernel at the end of a round copies the round's
+    // counters there and raises a sequence number the host spins on (vglb_counters_fetch) — a level / round boundary costs a
+    // PCIe write instead of cudaMemcpyAsync + cudaStreamSynchronize
+    unsigned long long *h_mailbox; // 64 words, word 63 = sequence number
+    unsigned long long mailbox_seq;
     int pr_carveout_set;   // pr_sweep_kernel's shared-memory carve-out preference has been set on this device
 };
 
@@ -158,6 +163,8 @@ constexpr int32_t vglb_tier_degree(int t)
     return t == 0 ? 4096 : t == 1 ? 32 : t == 2 ? 16 : t == 3 ? 8 : t == 4 ? 4 : t == 5 ? 2 : t == 6 ? 1 : 0;
 }
 
+// copy `words` (<= 56) 8-byte counters from device memory to ctx->h_counters, ordered after everything enqueued on ctx->stream
+int vglb_counters_fetch(vglb_ctx *ctx, const void *d_src, int words);
 int vglb_graph_compute_tiers(vglb_ctx *ctx, vglb_graph *g);
 void vglb_graph_set_unpartitioned(vglb_graph *g);
 int vglb_graph_derive_incoming(vglb_ctx *ctx, vglb_graph *g);

@@ -181,6 +181,9 @@ extern "C" int vglb_init(int device, vglb_ctx **out_ctx)
     CUDA_TRY(cudaEventCreate(&ctx->ev_start));
     CUDA_TRY(cudaEventCreate(&ctx->ev_stop));
     CUDA_TRY(cudaMallocHost((void **)&ctx->h_counters, 64 * sizeof(int64_t)));
+    CUDA_TRY(cudaHostAlloc((void **)&ctx->h_mailbox, 64 * sizeof(unsigned long long), cudaHostAllocMapped));
+    memset(ctx->h_mailbox, 0, 64 * sizeof(unsigned long long));
+    ctx->mailbox_seq = 0;
     CUDA_TRY(vglb_dev_alloc((void **)&ctx->d_counters, 64 * sizeof(int64_t)));
     CUDA_TRY(cudaMemset(ctx->d_counters, 0, 64 * sizeof(int64_t)));
     ctx->flush_bytes = ctx->l2_bytes * 2 > (size_t)(256u << 20) ? ctx->l2_bytes * 2 : (size_t)(256u << 20);
@@ -197,6 +200,7 @@ extern "C" int vglb_finalize(vglb_ctx *ctx)
     if (ctx->d_flush) vglb_dev_free(ctx->d_flush);
     vglb_dev_free(ctx->d_counters);
     cudaFreeHost(ctx->h_counters);
+    cudaFreeHost(ctx->h_mailbox);
     cudaEventDestroy(ctx->ev_start);
     cudaEventDestroy(ctx->ev_stop);
     cudaStreamDestroy(ctx->stream);
@@ -211,6 +215,48 @@ extern "C" int vglb_synchronize(vglb_ctx *ctx)
 {
     VGLB_REQUIRE(ctx != NULL, "vglb_synchronize: ctx is NULL");
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return VGLB_OK;
+}
+
+// ---- counter mailbox --------------------------------------------------------------------------------------------------
+__global__ void counters_publish_kernel(const unsigned long long *__restrict__ src, int words, volatile unsigned long long *mailbox,
+                                        unsigned long long seq)
+{
+    if ((int)threadIdx.x < words) mailbox[threadIdx.x] = src[threadIdx.x];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) mailbox[63] = seq;
+}
+
+int vglb_counters_fetch(vglb_ctx *ctx, const void *d_src, int words)
+{
+    VGLB_REQUIRE(words > 0 && words <= 56, "vglb_counters_fetch: at most 56 counters");
+    static int use_mailbox = -1;
+    if (use_mailbox < 0) use_mailbox = getenv("VGLB_NO_MAILBOX") ? 0 : 1; // developer knob: plain memcpy + stream sync
+    if (!use_mailbox)
+    {
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_counters, d_src, (size_t)words * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return VGLB_OK;
+    }
+    const unsigned long long seq = ++ctx->mailbox_seq;
+    counters_publish_kernel<<<1, 64, 0, ctx->stream>>>((const unsigned long long *)d_src, words, ctx->h_mailbox, seq);
+    KERNEL_TRY();
+    volatile unsigned long long *flag = ctx->h_mailbox + 63;
+    for (unsigned spins = 1;; spins++)
+    {
+        if (*flag == seq) break;
+        if ((spins & 0x3ff) == 0) // every ~1000 probes: has the stream died (or finished without the flag being visible yet)?
+        {
+            cudaError_t q = cudaStreamQuery(ctx->stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady)
+            {
+                vglb_set_error("CUDA error %s while waiting for the round's counters", cudaGetErrorString(q));
+                return VGLB_ECUDA;
+            }
+        }
+    }
+    for (int i = 0; i < words; i++) ((unsigned long long *)ctx->h_counters)[i] = ctx->h_mailbox[i];
     return VGLB_OK;
 }
 

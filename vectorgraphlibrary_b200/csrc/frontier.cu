@@ -382,8 +382,8 @@ static int gnf_run(vglb_ctx *ctx, vglb_frontier *f, Pred pred)
     KERNEL_TRY();
     ctx->launches++;
     unsigned long long *h = (unsigned long long *)ctx->h_counters;
-    CUDA_TRY(cudaMemcpyAsync(h, counters, G_COUNT * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    int rc_fetch = vglb_counters_fetch(ctx, counters, G_COUNT);
+    if (rc_fetch != VGLB_OK) return rc_fetch;
     f->size = (int32_t)h[G_SIZE];
     f->neighbours = (int64_t)h[G_NEIGHBOURS];
     f->tier_size[0] = (int32_t)h[G_TIER0];

@@ -387,6 +387,173 @@ sssp_relax_flat_kernel(const int64_t *__restrict__ ptr, const int32_t *__restric
     if (lane == 0 && edges) atomicAdd(&counters[C_EDGES], (unsigned long long)edges);
 }
 
+// ---- device-resident rounds for small frontiers (one GPU) ---------------------------------------------------------------
+// Most rounds of a run are tiny: on the BASELINE graph 55 of 80 rounds relax fewer than 10^4 edges and cost ~30 us each —
+// a select launch, a relax launch and a host read-back that decides what to launch next. One CTA drains such a stretch on
+// the device instead: it keeps the frontier as an id list in shared memory, relaxes it (block-wide prefix sum of the
+// degrees, every thread walks the flat edge range), and builds the next list on the fly — the thread whose atomicMin wins
+// AND that is first to set the vertex's bit in the near bitmap appends it (the bitmap, empty when the drain starts, is the
+// membership test). It returns to the host when the list runs empty (the near bucket is done: the host moves the
+// threshold), or outgrows one CTA (the bits already set in the near bitmap ARE the pending list: the regular select /
+// relax kernels take over). Same relaxations, same fixed point.
+#define SSSP_DRAIN_THREADS 1024
+#define SSSP_DRAIN_MAX_ROWS 1024   // one row per thread for the prefix sum
+#define SSSP_DRAIN_MAX_EDGES 65536 // edges one CTA relaxes per round
+#define SSSP_DRAIN_LIST 2048
+enum { DRAIN_NOT_STARTED = 0, DRAIN_EMPTY = 1, DRAIN_PENDING = 2 };
+// result slots in the counter block (after the 2 * C_COUNT + 1 words the host loop reads)
+enum { DR_REASON = 2 * C_COUNT + 2, DR_ROUNDS, DR_ROWS, DR_END };
+
+__global__ void __launch_bounds__(SSSP_DRAIN_THREADS)
+sssp_drain_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, const float *__restrict__ wgt, TierQueues cq,
+                  int32_t n_big, int32_t n_mid, int32_t n_small, uint32_t *__restrict__ dist, uint32_t *__restrict__ near_bm,
+                  uint32_t *__restrict__ far_bm, uint32_t threshold_bits, unsigned long long *counters)
+{
+    __shared__ int32_t s_list[2][SSSP_DRAIN_LIST];
+    __shared__ int32_t s_prefix[SSSP_DRAIN_MAX_ROWS + 1];
+    __shared__ int64_t s_start[SSSP_DRAIN_MAX_ROWS];
+    __shared__ float s_du[SSSP_DRAIN_MAX_ROWS];
+    __shared__ int32_t s_warp_tot[32];
+    __shared__ int s_next_n, s_overflow;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int n_cur = n_big + n_mid + n_small, cur = 0;
+    if (tid < n_cur) s_list[0][tid] = tid < n_big ? cq.q[0][tid] : (tid < n_big + n_mid ? cq.q[1][tid - n_big] : cq.q[2][tid - n_big - n_mid]);
+    long long edges = 0, rows = 0;
+    int rounds = 0, reason = DRAIN_NOT_STARTED;
+    __syncthreads();
+    for (;;)
+    {
+        // degrees of the current list and their block-wide exclusive prefix sum
+        int32_t u = -1;
+        int64_t start = 0;
+        int deg = 0;
+        if (tid < n_cur)
+        {
+            u = s_list[cur][tid];
+            start = ptr[u];
+            deg = (int)(ptr[u + 1] - start);
+        }
+        int incl = deg;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp_tot[warp] = incl;
+        if (tid == 0)
+        {
+            s_next_n = 0;
+            s_overflow = 0;
+        }
+        __syncthreads();
+        int warp_base = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 32; w++)
+        {
+            const int t = s_warp_tot[w];
+            if (w < warp) warp_base += t;
+            total += t;
+        }
+        if (total > SSSP_DRAIN_MAX_EDGES)
+        {
+            // too much for one CTA. Round 0: nothing has been touched, the queue the host selected is still valid (the host
+            // launches the regular relax). Later rounds: the list's bits are still set in the near bitmap.
+            if (rounds > 0) reason = DRAIN_PENDING;
+            break;
+        }
+        if (tid < n_cur)
+        {
+            // pop: the vertex leaves the due sets before its distance is read (a later drop re-queues it)
+            const uint32_t bit = 1u << (u & 31);
+            if (rounds > 0) atomicAnd(&near_bm[u >> 5], ~bit);
+            if (far_bm[u >> 5] & bit) atomicAnd(&far_bm[u >> 5], ~bit);
+            s_prefix[tid] = warp_base + incl - deg;
+            s_start[tid] = start;
+        }
+        if (tid == 0) s_prefix[n_cur] = total;
+        __threadfence_block();
+        __syncthreads();
+        if (tid < n_cur) s_du[tid] = __uint_as_float(dist[u]);
+        __syncthreads();
+        const int nxt = cur ^ 1;
+        // 4 independent edges per thread and step (index / weight loads, then the distance gathers, then the atomics): one CTA
+        // has little parallelism to hide latency with, so the loads of a step must not wait for each other
+        for (int idx0 = tid; idx0 < total; idx0 += SSSP_DRAIN_THREADS * 4)
+        {
+            int32_t v[4];
+            uint32_t c[4], dv[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+                const int idx = idx0 + k * SSSP_DRAIN_THREADS;
+                v[k] = -1;
+                c[k] = 0;
+                if (idx < total)
+                {
+                    int lo = 0, hi = n_cur; // largest j with prefix[j] <= idx
+                    while (hi - lo > 1)
+                    {
+                        const int mid = (lo + hi) >> 1;
+                        if (s_prefix[mid] <= idx) lo = mid;
+                        else hi = mid;
+                    }
+                    const int64_t p = s_start[lo] + (idx - s_prefix[lo]);
+                    v[k] = adj[p];
+                    c[k] = __float_as_uint(__fadd_rn(s_du[lo], wgt[p])); // shortest_paths.hpp:50-53
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) dv[k] = v[k] >= 0 ? dist[v[k]] : 0u;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+                if (v[k] < 0 || c[k] >= dv[k]) continue;
+                const uint32_t old = atomicMin(&dist[v[k]], c[k]);
+                if (c[k] < old)
+                {
+                    const uint32_t bit = 1u << (v[k] & 31);
+                    if (c[k] < threshold_bits)
+                    {
+                        if (!(atomicOr(&near_bm[v[k] >> 5], bit) & bit))
+                        {
+                            const int slot = atomicAdd(&s_next_n, 1);
+                            if (slot < SSSP_DRAIN_LIST) s_list[nxt][slot] = v[k];
+                            else s_overflow = 1;
+                        }
+                    }
+                    else if (!(far_bm[v[k] >> 5] & bit)) atomicOr(&far_bm[v[k] >> 5], bit);
+                }
+            }
+        }
+        edges += total;
+        rows += n_cur;
+        rounds++;
+        __syncthreads();
+        const int n_next = s_next_n;
+        if (n_next == 0)
+        {
+            reason = DRAIN_EMPTY;
+            break;
+        }
+        if (s_overflow || n_next > SSSP_DRAIN_MAX_ROWS)
+        {
+            reason = DRAIN_PENDING;
+            break;
+        }
+        n_cur = n_next;
+        cur = nxt;
+        __syncthreads();
+    }
+    if (tid == 0)
+    {
+        counters[C_EDGES] += (unsigned long long)edges;
+        counters[DR_REASON] = (unsigned long long)reason;
+        counters[DR_ROUNDS] = (unsigned long long)rounds;
+        counters[DR_ROWS] = (unsigned long long)rows;
+    }
+}
+
 // frontier selection of one round (generate_new_frontier, shortest_paths.hpp:58-66) from the due bitmaps: one thread
 // per 32-vertex word. FAR = false: every bit of the near bitmap is due and below the threshold — the word is taken and
 // cleared (and the same bits are cleared in the far bitmap: the vertex is being relaxed with a smaller distance).
@@ -717,11 +884,23 @@ static int sssp_run(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, int32_
     const int big_chunks = (int)ceil_div64(g->max_degree > 0 ? g->max_degree : 1, SSSP_BIG_CHUNK);
     bool from_far = false, far_nonempty = false;
     long long tot_queued_global = 0;
+    const bool use_drain = !part && getenv("VGLB_SSSP_NO_DRAIN") == NULL; // developer knob: every round through the host
+    bool near_known_empty = false; // the drain ran the near bucket dry: the next near select would find nothing
     for (;;)
     {
         uint32_t tbits;
         if (threshold >= inf) tbits = 0xffffffffu; // everything that is due
         else memcpy(&tbits, &threshold, 4);
+        if (near_known_empty && !from_far)
+        {
+            // same decision as after a near select that queued nothing, without launching it
+            near_known_empty = false;
+            if (!split || (threshold >= inf && !far_nonempty)) break;
+            from_far = true;
+            if (threshold < inf) threshold += delta;
+            continue;
+        }
+        near_known_empty = false;
         if (from_far) sssp_select_kernel<true><<<select_grid, 256, 0, st>>>(near_bm, far_bm, dist + col0, rows, tbits, b0, b1, cq, d_cnt);
         else sssp_select_kernel<false><<<select_grid, 256, 0, st>>>(near_bm, far_bm, dist + col0, rows, tbits, b0, b1, cq, d_cnt);
         KERNEL_TRY();
@@ -736,8 +915,16 @@ static int sssp_run(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, int32_
             rc = vglb_comm_allreduce_async(comm, d_cnt + C_COUNT, C_COUNT, VGLB_DT_I64, VGLB_OP_SUM);
             if (rc != VGLB_OK) return rc;
         }
-        CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, (2 * C_COUNT + 1) * 8, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
+        if (part)
+        {
+            CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, (2 * C_COUNT + 1) * 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+        }
+        else
+        {
+            rc = vglb_counters_fetch(ctx, d_cnt, 2 * C_COUNT + 1);
+            if (rc != VGLB_OK) return rc;
+        }
         CUDA_TRY(cudaMemsetAsync(d_cnt, 0, (2 * C_COUNT + 1) * 8, st));
         const int32_t n[3] = {(int32_t)h_cnt[C_NEXT_BIG], (int32_t)h_cnt[C_NEXT_MID], (int32_t)h_cnt[C_NEXT_SMALL]};
         const unsigned long long *gl = part ? h_cnt + C_COUNT : h_cnt; // whole-job sums drive the schedule
@@ -792,8 +979,34 @@ static int sssp_run(vglb_ctx *ctx, vglb_graph *g, const float *d_weights, int32_
             continue;
         }
         from_far = false;
-        tot_queued_global += n_cur;
         if (tbits != 0xffffffffu) far_nonempty = true; // this round relaxes against a finite threshold: it may park vertices
+        if (use_drain && n_cur <= SSSP_DRAIN_MAX_ROWS)
+        {
+            // a small frontier: one CTA runs this round and the following ones on the device until the bucket is empty or the
+            // frontier has outgrown it
+            sssp_drain_kernel<<<1, SSSP_DRAIN_THREADS, 0, st>>>(g->d_out_ptr, g->d_out_adj, d_weights, cq, n[0], n[1], n[2], dist, near_bm,
+                                                               far_bm, tbits, d_cnt);
+            KERNEL_TRY();
+            ctx->launches++;
+            rc = vglb_counters_fetch(ctx, d_cnt, DR_END);
+            if (rc != VGLB_OK) return rc;
+            CUDA_TRY(cudaMemsetAsync(d_cnt, 0, DR_END * 8, st));
+            const int reason = (int)h_cnt[DR_REASON];
+            if (reason != DRAIN_NOT_STARTED)
+            {
+                tot_edges += (int64_t)h_cnt[C_EDGES];
+                rounds += (int64_t)h_cnt[DR_ROUNDS];
+                tot_rows += (int64_t)h_cnt[DR_ROWS];
+                tot_next += (int64_t)h_cnt[DR_ROWS];
+                tot_queued_global += (long long)h_cnt[DR_ROWS];
+                near_known_empty = reason == DRAIN_EMPTY;
+                if (trace) fprintf(stderr, "sssp drain: %lld rounds, %lld rows, %lld edges on the device, %s\n", (long long)h_cnt[DR_ROUNDS],
+                                   (long long)h_cnt[DR_ROWS], (long long)h_cnt[C_EDGES], near_known_empty ? "bucket empty" : "frontier outgrew one CTA");
+                continue;
+            }
+            // (the few rows are too long for one CTA: the regular relax below takes them)
+        }
+        tot_queued_global += n_cur;
         if (n_local > 0)
         {
             // queue entries per warp: 32 when the frontier is large, fewer when it would leave SMs idle
