@@ -32,11 +32,15 @@ static double trace_now()
     return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
+// direction heuristic of the reference (gpu_change_state, change_state.hpp:5-6,100-141): ALPHA 15, BETA 18
+#define BFS_DEFAULT_ALPHA 15
+#define BFS_DEFAULT_BETA 18
 #define BFS_THREADS 256
 #define BFS_SMALL_LANES 8
 #define BFS_BU_PROBE 4       // in-neighbours probed per batch by one lane
 #define BFS_BU_PROBE_MAX 16  // lane-private probes before the warp takes the row over
-#define BFS_BIG_CHUNK 8192 // a row with >= 4096 edges is expanded by one CTA per chunk of this many edges
+#define BFS_BIG_CHUNK 8192 // a "big" row is expanded by CTAs, one per chunk of this many edges
+#define BFS_BIG_DEGREE 512 // one GPU: rows with at least this many edges are big (a 2691-edge source row took one warp 150 us)
 
 // NT threads (a CTA, a warp or an 8-lane group) expand the out-row [s,e) of one frontier vertex.
 // Every thread of the warp must call this together (ballots inside); `e <= s` for idle groups.
@@ -127,7 +131,9 @@ __device__ __forceinline__ void td_expand(const int64_t *__restrict__ ptr, const
         }
         uint32_t seen[BFS_TD_UNROLL];
 #pragma unroll
-        for (int k = 0; k < BFS_TD_UNROLL; k++) seen[k] = v[k] >= 0 ? visited[v[k] >> 5] : 0xffffffffu;
+        // (read through L2: a word cached in L1 stays stale for the rest of the kernel and every stale "unvisited" costs an
+        // atomic that cannot win — a third of the atomics of a big level)
+        for (int k = 0; k < BFS_TD_UNROLL; k++) seen[k] = v[k] >= 0 ? __ldcg(&visited[v[k] >> 5]) : 0xffffffffu;
 #pragma unroll
         for (int k = 0; k < BFS_TD_UNROLL; k++)
         {
@@ -197,38 +203,63 @@ bfs_td_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     long long edges = 0, mf = 0;
     int found = 0;
-    // hubs (>= 4096 edges; the largest rows of a scale-26 Kronecker graph have > 10^6): `hub_ctas` CTAs share every hub row
-    // of the frontier, BFS_BIG_CHUNK edges at a time — chunk j of the i-th queued hub goes to CTA (j + 7 i) mod hub_ctas.
-    // (One CTA per (row, chunk slot of the LONGEST row) launched hundreds of thousands of empty CTAs when a few thousand
-    // mid-sized hubs were queued: 0.78 ms for an 18 M-edge level.) Row ranges are staged through shared memory 256 at a time.
+    // hubs (>= 4096 edges; the largest rows of a scale-26 Kronecker graph have > 10^6): the queued hub rows are cut into
+    // BFS_BIG_CHUNK-edge chunks and the chunks are dealt round-robin to `hub_ctas` CTAs. Every CTA stages 256 row ranges at a
+    // time in shared memory, scans their chunk counts (block prefix sum) and binary-searches the rows of the chunks it owns —
+    // no CTA is launched for a chunk that does not exist (one CTA per (row, chunk slot of the LONGEST row) launched
+    // hundreds of thousands of empty CTAs: 0.78 ms for an 18 M-edge level) and no CTA walks rows it has no chunk of.
     const int big_blocks = hub_ctas;
     if (b < big_blocks)
     {
         __shared__ int64_t s_row_start[BFS_THREADS], s_row_end[BFS_THREADS];
+        __shared__ int s_chunk_prefix[BFS_THREADS + 1];
+        __shared__ int s_warp_chunks[BFS_THREADS / 32];
+        long long chunk_base = 0; // chunks of the batches before this one
         for (int base = 0; base < n_big; base += BFS_THREADS)
         {
             __syncthreads();
+            int nch = 0;
             if (base + (int)threadIdx.x < n_big)
             {
                 const int32_t u = cq.q[0][base + threadIdx.x];
-                s_row_start[threadIdx.x] = ptr[u];
-                s_row_end[threadIdx.x] = ptr[u + 1];
+                const int64_t rs = ptr[u], re = ptr[u + 1];
+                s_row_start[threadIdx.x] = rs;
+                s_row_end[threadIdx.x] = re;
+                nch = (int)((re - rs + BFS_BIG_CHUNK - 1) / BFS_BIG_CHUNK);
             }
+            int incl = nch;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) s_warp_chunks[warp] = incl;
+            __syncthreads();
+            int wbase = 0;
+#pragma unroll
+            for (int w = 0; w < BFS_THREADS / 32; w++)
+                if (w < warp) wbase += s_warp_chunks[w];
+            s_chunk_prefix[threadIdx.x + 1] = wbase + incl;
+            if (threadIdx.x == 0) s_chunk_prefix[0] = 0;
             __syncthreads();
             const int cnt = min(BFS_THREADS, n_big - base);
-            for (int k = 0; k < cnt; k++)
+            const int total = s_chunk_prefix[cnt];
+            int first = (int)((b - chunk_base % hub_ctas + hub_ctas) % hub_ctas);
+            for (int c = first; c < total; c += hub_ctas)
             {
-                const int64_t rs = s_row_start[k], re = s_row_end[k];
-                const int nchunks = (int)((re - rs + BFS_BIG_CHUNK - 1) / BFS_BIG_CHUNK);
-                int first = (b - (int)(((long long)(base + k) * 7) % hub_ctas)) % hub_ctas;
-                if (first < 0) first += hub_ctas;
-                for (int j = first; j < nchunks; j += hub_ctas)
+                int lo = 0, hi = cnt; // row k with prefix[k] <= c < prefix[k + 1]
+                while (hi - lo > 1)
                 {
-                    const int64_t s = rs + (int64_t)j * BFS_BIG_CHUNK, e = min(re, s + BFS_BIG_CHUNK);
-                    if (threadIdx.x == 0) edges += e - s;
-                    td_expand<BFS_THREADS, MODE>(ptr, adj, s, e, threadIdx.x, visited, levels, next_level, b0, b1, nq, counters, mf, A, found);
+                    const int mid = (lo + hi) >> 1;
+                    if (s_chunk_prefix[mid] <= c) lo = mid;
+                    else hi = mid;
                 }
+                const int64_t s = s_row_start[lo] + (int64_t)(c - s_chunk_prefix[lo]) * BFS_BIG_CHUNK, e = min(s_row_end[lo], s + BFS_BIG_CHUNK);
+                if (threadIdx.x == 0) edges += e - s;
+                td_expand<BFS_THREADS, MODE>(ptr, adj, s, e, threadIdx.x, visited, levels, next_level, b0, b1, nq, counters, mf, A, found);
             }
+            chunk_base += total;
         }
     }
     else if (b < big_blocks + blocks_mid)
@@ -313,16 +344,21 @@ bfs_apply_lists_kernel(const unsigned long long *const *__restrict__ peer_lists,
     if ((threadIdx.x & 31) == 0 && mf) atomicAdd(&counters[C_MF], (unsigned long long)mf);
 }
 
-// bottom-up step. A warp takes 32 consecutive words of the visited bitmap per pass: lane l loads word l (one coalesced
-// 128-byte read instead of 32 broadcast reads) and works out which of its 32 vertices still need a parent; words without
-// such vertices — most of them in the late levels — cost nothing more. Words with work are then processed one at a time
-// by the whole warp, lane l owning vertex l of the word: lane-private probes of the first in-neighbours, four at a time
-// (the four ids and then the four frontier bits are independent loads), then warp-cooperative scans of the long rows
-// with ballot early exit. Bitmap words are written without atomics; in-rows list sources hubs-first.
-#define BFS_BU_WORDS 4
+// bottom-up step. A warp takes 32 consecutive words of the visited bitmap per pass (1024 vertices): lane l loads word l (one
+// coalesced 128-byte read) and works out which of its 32 vertices still need a parent (unvisited, with in-edges); groups
+// without such vertices — most of them in the late levels — cost nothing more. The candidates are then COMPACTED through
+// shared memory (lane l deposits the bit positions of its word behind a warp prefix sum of the popcounts), so that the probe
+// phase runs with every lane on a real candidate whatever the density: in the first bottom-up level half of the vertices have
+// no in-edges and later levels have a handful of candidates per word — one lane per bit position ran at 25-50 % SIMD
+// efficiency and the kernel was issue-bound (63 % of the issue slots, 280 instructions per 32 vertices). Per candidate:
+// lane-private probes of the first in-neighbours, BFS_BU_PROBE at a time (the ids and then the frontier bits are independent
+// loads), BFS_BU_CAND candidates in flight per lane; rows longer than BFS_BU_PROBE_MAX are finished warp-cooperatively, 256
+// neighbours per round trip, with ballot early exit. In-rows list sources hubs-first. Results go back through a per-warp
+// shared-memory copy of the 32 words, so bitmap words are written without global atomics.
+#define BFS_BU_CAND 4        // candidates in flight per lane
 #define BFS_BU_LONG_UNROLL 8
 #ifndef BFS_BU_MIN_CTAS
-#define BFS_BU_MIN_CTAS 4 // A/B on Kronecker s26: 4 CTAs/SM (60 registers) 1.48-2.02 ms, 5 (48 regs) +3 %, 6 (40 regs, spills) +20 %
+#define BFS_BU_MIN_CTAS 4 // A/B on Kronecker s26 (first version): 4 CTAs/SM 1.48-2.02 ms, 5 (48 regs) +3 %, 6 (40 regs, spills) +20 %
 #endif
 
 __global__ void __launch_bounds__(BFS_THREADS, BFS_BU_MIN_CTAS)
@@ -331,12 +367,15 @@ bfs_bu_kernel(const int64_t *__restrict__ in_ptr, const int32_t *__restrict__ in
               int32_t *__restrict__ levels, int32_t next_level, unsigned long long *counters)
 {
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
+    __shared__ uint16_t s_cand[BFS_THREADS / 32][1024]; // offsets (0..1023) of the group's candidates, ascending
+    __shared__ uint32_t s_found[BFS_THREADS / 32][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t nwords = ((int64_t)V + 31) >> 5;
-    long long edges = 0, rows = 0;
-    int found_total = 0;
+    uint16_t *cand = s_cand[wib];
+    uint32_t *fnd_words = s_found[wib];
+    int edges = 0, rows = 0, found_total = 0;
     for (int64_t wbase = warp * 32; wbase < nwords; wbase += nwarps * 32)
     {
         const int64_t wl = wbase + lane;
@@ -348,86 +387,104 @@ bfs_bu_kernel(const int64_t *__restrict__ in_ptr, const int32_t *__restrict__ in
             // vertices without in-edges can never be found from below (half of a Kronecker graph): not even their row
             // pointers are read
             unv_l = ~vis_l & valid & ~no_in_edges[wl];
-            if (unv_l == 0) next_bm[wl] = 0;
         }
-        unsigned work = __ballot_sync(FULL, unv_l != 0);
-        while (work)
+        int incl = __popc(unv_l);
+        const int cnt_l = incl;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
         {
-            // up to BFS_BU_WORDS words with work are in flight together: the pass is a chain of dependent memory accesses
-            // (row pointers -> first in-neighbours -> their frontier bits), so independent words hide each other's latency
-            int jw[BFS_BU_WORDS];
-            uint32_t unv[BFS_BU_WORDS];
-#pragma unroll
-            for (int t = 0; t < BFS_BU_WORDS; t++)
+            const int t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int total = __shfl_sync(FULL, incl, 31);
+        if (total == 0)
+        {
+            if (wl < nwords) next_bm[wl] = 0;
+            continue;
+        }
+        // deposit: lane l writes the offsets of its word's candidates behind the candidates of the lower words
+        {
+            int pos = incl - cnt_l;
+            uint32_t bits = unv_l;
+            while (bits)
             {
-                jw[t] = work ? __ffs(work) - 1 : -1;
-                work &= work - 1;
-                unv[t] = jw[t] >= 0 ? __shfl_sync(FULL, unv_l, jw[t]) : 0u;
+                const int bpos = __ffs(bits) - 1;
+                bits &= bits - 1;
+                cand[pos++] = (uint16_t)((lane << 5) | bpos);
             }
-            int64_t s[BFS_BU_WORDS], e[BFS_BU_WORDS];
+        }
+        fnd_words[lane] = 0;
+        __syncwarp();
+        rows += (lane == 0) ? total : 0;
+        const int64_t vbase = wbase << 5;
+        for (int i0 = 0; i0 < total; i0 += 32 * BFS_BU_CAND)
+        {
+            int off[BFS_BU_CAND];
+            int64_t s[BFS_BU_CAND];
+            int deg[BFS_BU_CAND];
 #pragma unroll
-            for (int t = 0; t < BFS_BU_WORDS; t++)
+            for (int c = 0; c < BFS_BU_CAND; c++)
             {
-                s[t] = 0;
-                e[t] = 0;
-                if ((unv[t] >> lane) & 1u)
+                const int idx = i0 + c * 32 + lane;
+                off[c] = idx < total ? (int)cand[idx] : -1;
+                s[c] = 0;
+                deg[c] = 0;
+                if (off[c] >= 0)
                 {
-                    const int64_t v = ((wbase + jw[t]) << 5) + lane;
-                    s[t] = in_ptr[v];
-                    e[t] = in_ptr[v + 1];
-                    rows++;
+                    const int64_t v = vbase + off[c];
+                    s[c] = in_ptr[v];
+                    deg[c] = (int)(in_ptr[v + 1] - s[c]);
                 }
             }
-            int32_t x[BFS_BU_WORDS][BFS_BU_PROBE];
+            int32_t x[BFS_BU_CAND][BFS_BU_PROBE];
 #pragma unroll
-            for (int t = 0; t < BFS_BU_WORDS; t++)
+            for (int c = 0; c < BFS_BU_CAND; c++)
 #pragma unroll
-                for (int k = 0; k < BFS_BU_PROBE; k++) x[t][k] = s[t] + k < e[t] ? in_adj[s[t] + k] : -1;
-            bool found[BFS_BU_WORDS];
+                for (int k = 0; k < BFS_BU_PROBE; k++) x[c][k] = k < deg[c] ? in_adj[s[c] + k] : -1;
+            bool fnd[BFS_BU_CAND];
 #pragma unroll
-            for (int t = 0; t < BFS_BU_WORDS; t++)
+            for (int c = 0; c < BFS_BU_CAND; c++)
             {
-                found[t] = false;
+                fnd[c] = false;
 #pragma unroll
                 for (int k = 0; k < BFS_BU_PROBE; k++)
-                    if (x[t][k] >= 0)
+                    if (x[c][k] >= 0)
                     {
                         edges++;
-                        found[t] |= bm_test(cur_bm, x[t][k]);
+                        fnd[c] |= bm_test(cur_bm, x[c][k]);
                     }
             }
 #pragma unroll
-            for (int t = 0; t < BFS_BU_WORDS; t++)
+            for (int c = 0; c < BFS_BU_CAND; c++)
             {
-                if (jw[t] < 0) break;
-                const int64_t w = wbase + jw[t];
-                bool fnd = found[t];
-                // further lane-private probes, four at a time, up to BFS_BU_PROBE_MAX in-neighbours
-                const int64_t pe = min(e[t], s[t] + BFS_BU_PROBE_MAX);
-                for (int64_t p = s[t] + BFS_BU_PROBE; p < pe && !fnd; p += BFS_BU_PROBE)
+                if (i0 + c * 32 >= total) break; // (uniform)
+                bool f = fnd[c];
+                // further lane-private probes, BFS_BU_PROBE at a time, up to BFS_BU_PROBE_MAX in-neighbours
+                const int dmax = min(deg[c], BFS_BU_PROBE_MAX);
+                for (int q = BFS_BU_PROBE; q < dmax && !f; q += BFS_BU_PROBE)
                 {
                     int32_t y[BFS_BU_PROBE];
 #pragma unroll
-                    for (int k = 0; k < BFS_BU_PROBE; k++) y[k] = p + k < pe ? in_adj[p + k] : -1;
+                    for (int k = 0; k < BFS_BU_PROBE; k++) y[k] = q + k < dmax ? in_adj[s[c] + q + k] : -1;
 #pragma unroll
                     for (int k = 0; k < BFS_BU_PROBE; k++)
                         if (y[k] >= 0)
                         {
                             edges++;
-                            fnd |= bm_test(cur_bm, y[k]);
+                            f |= bm_test(cur_bm, y[k]);
                         }
                 }
-                // rows longer than the probe: finished by the whole warp, 32 neighbours at a time
-                unsigned pending = __ballot_sync(FULL, !fnd && (s[t] + BFS_BU_PROBE_MAX < e[t]));
+                // rows longer than the probe: finished by the whole warp
+                unsigned pending = __ballot_sync(FULL, !f && deg[c] > BFS_BU_PROBE_MAX);
                 while (pending)
                 {
                     const int src_lane = __ffs(pending) - 1;
                     pending &= pending - 1;
-                    const int64_t ps = __shfl_sync(FULL, s[t], src_lane) + BFS_BU_PROBE_MAX;
-                    const int64_t pend = __shfl_sync(FULL, e[t], src_lane);
+                    const int64_t ps = __shfl_sync(FULL, s[c], src_lane) + BFS_BU_PROBE_MAX;
+                    const int64_t pend = ps - BFS_BU_PROBE_MAX + __shfl_sync(FULL, deg[c], src_lane);
                     bool hit = false;
-                    // BFS_BU_LONG_UNROLL x 32 neighbours per round trip: a vertex without a parent in the frontier (most of them in the
-                    // first bottom-up level) scans its whole in-row, and 32 edges per dependent load pair was the kernel's bottleneck
+                    // BFS_BU_LONG_UNROLL x 32 neighbours per round trip: a vertex without a parent in the frontier (most of them in
+                    // the first bottom-up level) scans its whole in-row, and 32 edges per dependent load pair is far too few
                     for (int64_t p0 = ps; p0 < pend; p0 += 32 * BFS_BU_LONG_UNROLL)
                     {
                         int32_t y[BFS_BU_LONG_UNROLL];
@@ -451,26 +508,31 @@ bfs_bu_kernel(const int64_t *__restrict__ in_ptr, const int32_t *__restrict__ in
                             break;
                         }
                     }
-                    if (lane == src_lane && hit) fnd = true;
+                    if (lane == src_lane && hit) f = true;
                 }
-                const uint32_t fmask = __ballot_sync(FULL, fnd);
-                if (fnd) levels[(w << 5) + lane] = next_level;
-                if (lane == jw[t])
+                if (f)
                 {
-                    next_bm[w] = fmask;
-                    if (fmask) visited[w] = vis_l | fmask;
-                    found_total += __popc(fmask);
+                    levels[vbase + off[c]] = next_level;
+                    atomicOr(&fnd_words[off[c] >> 5], 1u << (off[c] & 31));
                 }
             }
         }
+        __syncwarp();
+        if (wl < nwords)
+        {
+            const uint32_t fmask = fnd_words[lane];
+            next_bm[wl] = fmask;
+            if (fmask) visited[wl] = vis_l | fmask;
+            found_total += __popc(fmask);
+        }
+        __syncwarp();
     }
-    edges = warp_sum_i64(edges);
-    rows = warp_sum_i64(rows);
+    long long e64 = warp_sum_i64(edges), r64 = warp_sum_i64(rows);
     found_total = (int)warp_sum_i64(found_total);
     if (lane == 0)
     {
-        if (edges) atomicAdd(&counters[C_EDGES], (unsigned long long)edges);
-        if (rows) atomicAdd(&counters[C_ROWS], (unsigned long long)rows);
+        if (e64) atomicAdd(&counters[C_EDGES], (unsigned long long)e64);
+        if (r64) atomicAdd(&counters[C_ROWS], (unsigned long long)r64);
         if (found_total) atomicAdd(&counters[C_FOUND], (unsigned long long)found_total);
     }
 }
@@ -1083,14 +1145,25 @@ extern "C" int vglb_bfs(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t *d
         vglb_set_error("vglb_bfs: direction-optimising BFS needs a graph built with VGLB_GRAPH_WITH_INCOMING");
         return VGLB_EINVAL;
     }
-    const long long alpha = (opts && opts->alpha > 0) ? opts->alpha : 15; // change_state.hpp:5-6
-    const long long beta = (opts && opts->beta > 0) ? opts->beta : 18;
+    long long alpha = (opts && opts->alpha > 0) ? opts->alpha : BFS_DEFAULT_ALPHA;
+    long long beta = (opts && opts->beta > 0) ? opts->beta : BFS_DEFAULT_BETA;
+    if (!(opts && opts->alpha > 0) && getenv("VGLB_BFS_ALPHA")) alpha = atoll(getenv("VGLB_BFS_ALPHA")); // developer knobs (A/B runs)
+    if (!(opts && opts->beta > 0) && getenv("VGLB_BFS_BETA")) beta = atoll(getenv("VGLB_BFS_BETA"));
+    if (alpha < 1) alpha = 1;
+    if (beta < 1) beta = 1;
     CUDA_TRY(cudaSetDevice(ctx->device));
     int rc = bfs_prepare(ctx, g);
     if (rc != VGLB_OK) return rc;
     const int64_t launches0 = ctx->launches;
     const int32_t V = g->V;
-    const int32_t b0 = g->tier_border[0], b1 = g->tier_border[1];
+    if (g->bfs_big_border_plus1 == 0) // first id with fewer than BFS_BIG_DEGREE edges (ids are degree-sorted), once per graph
+    {
+        int32_t border = 0;
+        rc = vglb_graph_threshold_vertex(ctx, g, BFS_BIG_DEGREE, &border);
+        if (rc != VGLB_OK) return rc;
+        g->bfs_big_border_plus1 = border + 1;
+    }
+    const int32_t b0 = g->bfs_big_border_plus1 - 1, b1 = g->tier_border[1] > b0 ? g->tier_border[1] : b0;
     const size_t words = ((size_t)V + 31) / 32;
     unsigned long long *d_cnt = (unsigned long long *)ctx->d_counters;
     unsigned long long *h_cnt = (unsigned long long *)ctx->h_counters;
