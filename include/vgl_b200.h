@@ -154,6 +154,12 @@ int vglb_varray_reorder_u32(vglb_ctx *ctx, vglb_graph *g, const uint32_t *d_in, 
 /* EdgesArray weights for every out-CSR position from vglb_edge_weight(orig_src, orig_dst, seed)
  * (reference: EdgesArray::set_all_random, vect_csr_edges_array.hpp:49-65) */
 int vglb_earray_fill_synthetic_weights(vglb_ctx *ctx, vglb_graph *g, uint64_t seed, float *d_weights);
+/* VGL_Graph::copy_outgoing_to_incoming_edges (vgl_graph/reorder.hpp:229-233 -> VectorCSRGraph::reorder_edges_gather,
+ * vect_csr/reorder.hpp:61-75): per-edge 4-byte values at outgoing-CSR positions -> the positions of the same edges in the
+ * incoming CSR, the second segment of an EdgesArray ([outgoing | incoming], vect_csr_edges_array.hpp:49-65), so that gather-
+ * direction operators (pull SSSP, shortest_paths.hpp:168-291) can index weights with global_edge_pos. Derives the incoming
+ * CSR if the graph was built without it; the permutation is computed on first use and kept with the graph. */
+int vglb_earray_mirror_out_to_in_u32(vglb_ctx *ctx, vglb_graph *g, const uint32_t *d_out_values, uint32_t *d_in_values);
 /* per-vertex in-degree without self loops in SCATTER numbering (pr.hpp:28-73) */
 int vglb_graph_indegree_noloops(vglb_ctx *ctx, vglb_graph *g, int32_t *d_indeg);
 
@@ -254,6 +260,20 @@ int vglb_gnf_ne_u32(vglb_ctx *ctx, vglb_frontier *f, const uint32_t *d_a, const 
 int vglb_reduce_sum_i32(vglb_ctx *ctx, vglb_frontier *f, const int32_t *d_values, int64_t *out);
 int vglb_reduce_sum_f32(vglb_ctx *ctx, vglb_frontier *f, const float *d_values, double *out);
 int vglb_reduce_max_i32(vglb_ctx *ctx, vglb_frontier *f, const int32_t *d_values, int32_t *out);
+
+/* ---- result verification on the device (vgl_runtime/helpers/verify_results/verify_results.h) ----
+ * The reference's checkers reorder both arrays to ORIGINAL and compare on the host; here both arrays are device arrays in the
+ * same numbering (vglb_varray_reorder_u32) and only the verdict comes back.
+ *   vglb_verify_i32 / _f32       verify_results (:33-93): the `error count` of elements that are not are_same (:9-28: exact for
+ *                                int, |a - b| <= 100 * FLT_EPSILON for float)
+ *   vglb_verify_ranking_f32      verify_ranking_results (:97-148): mean |a - ref| (error_count = n unless it is < 1e-4), plus the
+ *                                relative L1 distance sum|a - ref| / sum|ref| that the parity bar of this backend is stated in
+ *   vglb_verify_components_i32   equal_components (:198-254): the two label arrays describe the same partition (labels in [0, n + 1]) */
+int vglb_verify_i32(vglb_ctx *ctx, const int32_t *d_a, const int32_t *d_b, int64_t n, int64_t *error_count);
+int vglb_verify_f32(vglb_ctx *ctx, const float *d_a, const float *d_b, int64_t n, int64_t *error_count);
+int vglb_verify_ranking_f32(vglb_ctx *ctx, const float *d_a, const float *d_ref, int64_t n, double *mean_abs_difference,
+                            double *relative_l1, int64_t *error_count);
+int vglb_verify_components_i32(vglb_ctx *ctx, const int32_t *d_a, const int32_t *d_b, int32_t n, int64_t *error_count);
 
 /* ---- multi-GPU: one process per GPU, 1D vertex partition, NCCL over NVLink ----------------------------------------
  * Reference: the MPI layer of the NEC backend — vgl_mpi_init (vgl_runtime/helpers/library_data/init.hpp:5-38), the

@@ -159,11 +159,20 @@ public:
     }
     __host__ __device__ inline _T &operator[](long long _idx) const { return ptr[_idx]; }
     __host__ __device__ inline _T *get_ptr() const { return ptr; }
-    // deterministic weights of the outgoing direction (EdgesArray::set_all_random twin)
+    // deterministic weights of the outgoing direction (EdgesArray::set_all_random twin), mirrored to the incoming segment the
+    // way set_all_random does (vect_csr_edges_array.hpp:49-65)
     void set_synthetic_weights(unsigned long long _seed)
     {
         static_assert(sizeof(_T) == 4, "synthetic weights are fp32");
         check(vglb_earray_fill_synthetic_weights(graph->rt.ctx, graph->handle, _seed, (float *)ptr));
+        if (graph->info.has_incoming) mirror_outgoing_to_incoming();
+    }
+    // VGL_Graph::copy_outgoing_to_incoming_edges (vgl_graph/reorder.hpp:229-233): values of the outgoing segment [0, E) ->
+    // the same edges' positions in the incoming segment [E, 2E), which gather-direction operators index with global_edge_pos
+    void mirror_outgoing_to_incoming()
+    {
+        static_assert(sizeof(_T) == 4, "the mirror moves 4-byte elements");
+        check(vglb_earray_mirror_out_to_in_u32(graph->rt.ctx, graph->handle, (const uint32_t *)ptr, (uint32_t *)(ptr + graph->get_edges_count())));
     }
 };
 

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Turn an .ncu-rep (from `ncu --set full`) into the short text summary that is committed under profiles/.
 
-    python scripts/ncu_summary.py gpurun_out/prof.ncu-rep > profiles/r1_pr_sweep_full.txt
+    python scripts/ncu_summary.py gpurun_out/prof.ncu-rep [--top N] > profiles/r1_pr_sweep_full.txt
+
+--top N keeps the N longest launches of the report (a capture of every launch of a run, of which the dominant one matters).
 """
 import csv
 import subprocess
@@ -40,13 +42,19 @@ KEYS = [
 
 def main():
     rep = sys.argv[1]
+    top = int(sys.argv[sys.argv.index("--top") + 1]) if "--top" in sys.argv else 0
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
     hdr, units = rows[hi], rows[hi + 1]
     print(f"# ncu --set full summary of {rep.split('/')[-1]} (raw page; per launch, --clock-control none)")
-    for r in rows[hi + 2:]:
-        print("kernel:", r[hdr.index("Kernel Name")])
+    body = rows[hi + 2:]
+    if top:
+        di = hdr.index("gpu__time_duration.sum")
+        body = sorted(body, key=lambda r: -float(r[di].replace(",", "")))[:top]
+        print(f"# the {top} longest of {len(rows) - hi - 2} captured launches")
+    for r in body:
+        print("kernel:", r[hdr.index("Kernel Name")], " launch id", r[hdr.index("ID")])
         for k in KEYS:
             if k in hdr:
                 i = hdr.index(k)

@@ -100,6 +100,11 @@ _SIGNATURES = {
     "vglb_varray_reorder_u32": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int]),
     "vglb_earray_fill_synthetic_weights": (C.c_int, [_P, _P, C.c_uint64, _P]),
     "vglb_graph_indegree_noloops": (C.c_int, [_P, _P, _P]),
+    "vglb_earray_mirror_out_to_in_u32": (C.c_int, [_P, _P, _P, _P]),
+    "vglb_verify_i32": (C.c_int, [_P, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "vglb_verify_f32": (C.c_int, [_P, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "vglb_verify_ranking_f32": (C.c_int, [_P, _P, _P, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "vglb_verify_components_i32": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(C.c_int64)]),
     "vglb_pagerank": (C.c_int, [_P, _P, C.c_int, C.c_float, _P, C.POINTER(Stats)]),
     "vglb_pagerank_ex": (C.c_int, [_P, _P, C.c_int, C.c_float, C.POINTER(PrOpts), _P, C.POINTER(Stats)]),
     "vglb_bfs": (C.c_int, [_P, _P, C.c_int32, _P, C.POINTER(BfsOpts), C.POINTER(Stats)]),
@@ -481,6 +486,13 @@ class Graph:
         _check(lib().vglb_earray_fill_synthetic_weights(self.ctx.h, self.h, seed, w.ptr))
         return w
 
+    def mirror_out_to_in(self, out_values: DeviceArray) -> DeviceArray:
+        """VGL_Graph::copy_outgoing_to_incoming_edges: per-edge values in outgoing-CSR order -> incoming-CSR order."""
+        assert out_values.dtype.itemsize == 4 and out_values.n == self.E
+        out = self.ctx.empty(self.E, out_values.dtype)
+        _check(lib().vglb_earray_mirror_out_to_in_u32(self.ctx.h, self.h, out_values.ptr, out.ptr))
+        return out
+
     def indegree_noloops(self) -> DeviceArray:
         d = self.ctx.empty(self.V, np.int32)
         _check(lib().vglb_graph_indegree_noloops(self.ctx.h, self.h, d.ptr))
@@ -519,6 +531,32 @@ class Graph:
         st = Stats()
         _check(lib().vglb_cc(self.ctx.h, self.h, labels.ptr, C.byref(st)))
         return labels, st
+
+
+def verify_results(ctx: "Context", a: DeviceArray, b: DeviceArray) -> int:
+    """verify_results (verify_results.h:33-93) on the device: the `error count` (0 = equal). int32 arrays compare exactly,
+    float32 arrays with the reference's are_same tolerance."""
+    assert a.n == b.n and a.dtype == b.dtype
+    out = C.c_int64()
+    fn = lib().vglb_verify_f32 if a.dtype == np.float32 else lib().vglb_verify_i32
+    _check(fn(ctx.h, a.ptr, b.ptr, a.n, C.byref(out)))
+    return out.value
+
+
+def verify_ranking_results(ctx: "Context", a: DeviceArray, ref: DeviceArray):
+    """verify_ranking_results (verify_results.h:97-148): (mean |a - ref|, relative L1, error count)."""
+    assert a.n == ref.n
+    diff, rel, err = C.c_double(), C.c_double(), C.c_int64()
+    _check(lib().vglb_verify_ranking_f32(ctx.h, a.ptr, ref.ptr, a.n, C.byref(diff), C.byref(rel), C.byref(err)))
+    return diff.value, rel.value, err.value
+
+
+def equal_components(ctx: "Context", a: DeviceArray, b: DeviceArray) -> int:
+    """equal_components (verify_results.h:198-254): error count, 0 = the label arrays describe the same partition."""
+    assert a.n == b.n
+    out = C.c_int64()
+    _check(lib().vglb_verify_components_i32(ctx.h, a.ptr, b.ptr, a.n, C.byref(out)))
+    return out.value
 
 
 class Frontier:

@@ -358,7 +358,7 @@ bfs_apply_lists_kernel(const unsigned long long *const *__restrict__ peer_lists,
 #define BFS_BU_CAND 4        // candidates in flight per lane
 #define BFS_BU_LONG_UNROLL 8
 #ifndef BFS_BU_MIN_CTAS
-#define BFS_BU_MIN_CTAS 4 // A/B on Kronecker s26 (first version): 4 CTAs/SM 1.48-2.02 ms, 5 (48 regs) +3 %, 6 (40 regs, spills) +20 %
+#define BFS_BU_MIN_CTAS 4 // 64 registers. A/B on Kronecker s26: 5 CTAs/SM (48 registers, one resident wave) 1.09-1.11 ms vs 1.06-1.07 ms
 #endif
 
 __global__ void __launch_bounds__(BFS_THREADS, BFS_BU_MIN_CTAS)

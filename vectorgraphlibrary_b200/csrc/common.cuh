@@ -84,6 +84,7 @@ struct vglb_graph
     int32_t *d_fwd; // orig -> sorted
     int32_t *d_bwd; // sorted -> orig
     int64_t *d_edge_order;
+    uint32_t *d_in_to_out_pos; // incoming-CSR position -> outgoing-CSR position of the same edge (verify.cu, built on first use)
     int32_t tier_degree[VGLB_NUM_TIERS];
     int32_t tier_border[VGLB_NUM_TIERS];
     // lazily created per-algorithm state (owned by the graph, freed with it)

@@ -259,7 +259,7 @@ void vglb_graph_free_fields(vglb_graph *g)
         vglb_dev_free(g->d_out_adj);
     }
     vglb_dev_free(g->d_in_ptr); vglb_dev_free(g->d_in_adj);
-    vglb_dev_free(g->d_fwd); vglb_dev_free(g->d_bwd); vglb_dev_free(g->d_edge_order);
+    vglb_dev_free(g->d_fwd); vglb_dev_free(g->d_bwd); vglb_dev_free(g->d_edge_order); vglb_dev_free(g->d_in_to_out_pos);
     vglb_dev_free(g->d_indeg_noloops); vglb_dev_free(g->d_pr_inv); vglb_dev_free(g->d_pr_contrib[0]); vglb_dev_free(g->d_pr_contrib[1]); vglb_dev_free(g->d_pr_dangling); vglb_dev_free(g->d_pr_tasks); vglb_dev_free(g->d_pr_piece_partial); vglb_dev_free(g->d_pr_piece_count); vglb_dev_free(g->d_pr_ve_adj); vglb_dev_free(g->d_pr_ve_ptr);
     vglb_dev_free(g->d_visited); vglb_dev_free(g->d_front_bm[0]); vglb_dev_free(g->d_front_bm[1]);
     vglb_dev_free(g->d_queue[0]); vglb_dev_free(g->d_queue[1]); vglb_dev_free(g->d_scratch_i32);

@@ -271,6 +271,44 @@ __device__ __forceinline__ void sssp_relax_one(uint32_t *__restrict__ dist, uint
     }
 }
 
+// relax SSSP_FLAT_UNROLL edges whose destination distances have been gathered, in PHASES: all atomicMin of the step (they
+// return the old value, so each is a full round trip), then the due-bitmap words of the winners, then the atomicOr marks.
+// Edge by edge the winners of a step paid up to 2 x SSSP_FLAT_UNROLL dependent round trips; in phases two. (The gathers are
+// issued together before any atomic for the same reason: an atomic orders the loads behind it.)
+template <int N>
+__device__ __forceinline__ void sssp_relax_batch(uint32_t *__restrict__ dist, uint32_t *__restrict__ near_bm, uint32_t *__restrict__ far_bm,
+                                                 uint32_t *__restrict__ changed_bm, int32_t col0, int32_t vp, uint32_t threshold_bits,
+                                                 const int32_t (&v)[N], const uint32_t (&c)[N], const uint32_t (&seen)[N])
+{
+    uint32_t old[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) old[k] = (v[k] >= 0 && c[k] < seen[k]) ? atomicMin(&dist[v[k]], c[k]) : 0u;
+    uint32_t *word_ptr[N];
+    uint32_t word[N], bit[N];
+#pragma unroll
+    for (int k = 0; k < N; k++)
+    {
+        word_ptr[k] = NULL;
+        word[k] = 0xffffffffu;
+        bit[k] = 0;
+        if (c[k] < old[k]) // (old is 0 for the edges that did not try)
+        {
+            // a vertex of this rank's slice (every vertex on one GPU) becomes due here; a vertex owned by a peer is flagged in
+            // the changed bitmap, whose slices go to the owners after the round
+            const uint32_t r = (uint32_t)(v[k] - col0);
+            const bool local = r < (uint32_t)vp;
+            uint32_t *bm = local ? (c[k] < threshold_bits ? near_bm : far_bm) : changed_bm;
+            const uint32_t i = local ? r : (uint32_t)v[k];
+            word_ptr[k] = bm + (i >> 5);
+            bit[k] = 1u << (i & 31);
+            word[k] = *word_ptr[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < N; k++)
+        if (!(word[k] & bit[k])) atomicOr(word_ptr[k], bit[k]);
+}
+
 __global__ void __launch_bounds__(SSSP_THREADS)
 sssp_relax_flat_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, const float *__restrict__ wgt,
                        TierQueues cq, int32_t n_big, int32_t big_chunks, int32_t n_mid, int32_t n_small, int32_t per_warp_mid, int32_t per_warp,
@@ -308,9 +346,10 @@ sssp_relax_flat_kernel(const int64_t *__restrict__ ptr, const int32_t *__restric
                     c[k] = __float_as_uint(__fadd_rn(du, ld_stream_f32(wgt + p, pol)));
                 }
             }
+            uint32_t seen[SSSP_FLAT_UNROLL];
 #pragma unroll
-            for (int k = 0; k < SSSP_FLAT_UNROLL; k++)
-                if (v[k] >= 0) sssp_relax_one(dist, near_bm, far_bm, changed_bm, col0, vp, threshold_bits, v[k], c[k]);
+            for (int k = 0; k < SSSP_FLAT_UNROLL; k++) seen[k] = v[k] >= 0 ? dist[v[k]] : 0u;
+            sssp_relax_batch<SSSP_FLAT_UNROLL>(dist, near_bm, far_bm, changed_bm, col0, vp, threshold_bits, v, c, seen);
         }
     }
     else
@@ -347,10 +386,13 @@ sssp_relax_flat_kernel(const int64_t *__restrict__ ptr, const int32_t *__restric
             const int excl = incl - deg;
             const int total = __shfl_sync(FULL, incl, 31);
             if (lane == 0) edges = total;
+            // per step: index / weight loads, then the step's distance gathers together, then its atomics (an atomic orders the
+            // loads behind it). A/B on the BASELINE graph: prefetching step i + 1 before step i's gathers (40 registers, 75 %
+            // occupancy) was 3 % SLOWER than this (32 registers, full occupancy): the kernel lives on resident warps.
             for (int base = 0; base < total; base += 32 * SSSP_FLAT_UNROLL)
             {
                 int32_t v[SSSP_FLAT_UNROLL];
-                float cand[SSSP_FLAT_UNROLL];
+                uint32_t c[SSSP_FLAT_UNROLL], seen[SSSP_FLAT_UNROLL];
 #pragma unroll
                 for (int k = 0; k < SSSP_FLAT_UNROLL; k++)
                 {
@@ -366,20 +408,17 @@ sssp_relax_flat_kernel(const int64_t *__restrict__ ptr, const int32_t *__restric
                     const int exj = __shfl_sync(FULL, excl, j);
                     const float duj = __shfl_sync(FULL, du, j);
                     v[k] = -1;
-                    cand[k] = 0.f;
+                    c[k] = 0;
                     if (idx < total)
                     {
                         const int64_t p = sj + (idx - exj);
                         v[k] = ld_stream_s32(adj + p, pol);
-                        cand[k] = __fadd_rn(duj, ld_stream_f32(wgt + p, pol)); // shortest_paths.hpp:50-53
+                        c[k] = __float_as_uint(__fadd_rn(duj, ld_stream_f32(wgt + p, pol))); // shortest_paths.hpp:50-53
                     }
                 }
 #pragma unroll
-                for (int k = 0; k < SSSP_FLAT_UNROLL; k++)
-                {
-                    if (v[k] >= 0)
-                        sssp_relax_one(dist, near_bm, far_bm, changed_bm, col0, vp, threshold_bits, v[k], __float_as_uint(cand[k]));
-                }
+                for (int k = 0; k < SSSP_FLAT_UNROLL; k++) seen[k] = v[k] >= 0 ? dist[v[k]] : 0u;
+                sssp_relax_batch<SSSP_FLAT_UNROLL>(dist, near_bm, far_bm, changed_bm, col0, vp, threshold_bits, v, c, seen);
             }
         }
     }
