@@ -462,7 +462,7 @@ def ours(args):
     headline = "pr" if config5 else args.workload
     scale = args.scale or (28 if config5 else WORKLOADS[headline][1])
     head_weak = weak and not config5
-    res = B.run_workload(headline, scale, args.steps, args.warmup, weak=head_weak, sample_clocks=True)
+    res = B.run_workload(headline, scale, args.steps, args.warmup, weak=head_weak, sample_clocks=True, td_only=args.top_down_only)
 
     line = None
     if rank == 0:
@@ -552,6 +552,7 @@ def main():
     ap.add_argument("--cpu-scale", type=int, default=0, help="scale of the CPU arm's graph (default: the workload's own where it fits)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="headline only (profiling runs)")
+    ap.add_argument("--top-down-only", action="store_true", help="BFS workloads: no direction switch (the reference's BFS::vgl_top_down)")
     ap.add_argument("--extras-budget", type=float, default=420.0, help="seconds after which no further extra workload is started")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

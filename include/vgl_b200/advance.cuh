@@ -225,7 +225,9 @@ __device__ __forceinline__ void advance_batch(const CsrView &g, bool have, int32
 
 struct AllActivePlan
 {
-    int32_t hub_rows, hub_chunks;  // blocks [0, hub_rows * hub_chunks): hub rows
+    int32_t hub_rows, hub_chunks;  // blocks [0, hub_blocks): hub rows — one CTA per row (vertex ops: hub_chunks = 0) or one per
+                                   // kHubChunk edges of the hub region's flat edge range [0, flat_edge0) (hub_chunks CTAs)
+    int32_t hub_blocks;
     int32_t flat_blocks;           // then the merge-path region: rows [hub_rows, nz_rows)
     int32_t zero_blocks;           // then rows without edges (vertex ops only)
     int32_t nz_rows;               // rows with at least one edge
@@ -239,15 +241,15 @@ inline AllActivePlan plan_all_active(const CsrView &g, int64_t edges, int64_t hu
     AllActivePlan P;
     P.hub_rows = g.tier_border[0];
     constexpr bool kNoOps = is_no_vertex_op<PreOp>::value && is_no_vertex_op<PostOp>::value;
-    P.hub_chunks = kNoOps ? (int32_t)((g.max_degree + kHubChunk - 1) / kHubChunk) : 1;
-    if (P.hub_chunks < 1) P.hub_chunks = 1;
+    P.hub_chunks = kNoOps ? (int32_t)((hub_edges + kHubChunk - 1) / kHubChunk) : 0;
+    P.hub_blocks = kNoOps ? P.hub_chunks : P.hub_rows;
     P.nz_rows = g.tier_border[kNumTiers - 2];
     P.flat_edge0 = hub_edges;
     P.flat_edges = edges - hub_edges;
     const int64_t warps = (P.flat_edges + kWarpEdges - 1) / kWarpEdges;
     P.flat_blocks = (int32_t)((warps + kAdvWarps - 1) / kAdvWarps);
     P.zero_blocks = kNoOps ? 0 : (int32_t)(((int64_t)(g.V - P.nz_rows) + kAdvThreads * 8 - 1) / (kAdvThreads * 8));
-    P.blocks = (int64_t)P.hub_rows * P.hub_chunks + P.flat_blocks + P.zero_blocks;
+    P.blocks = (int64_t)P.hub_blocks + P.flat_blocks + P.zero_blocks;
     return P;
 }
 
@@ -259,10 +261,29 @@ advance_all_active_kernel(const CsrView g, const AllActivePlan P, long long edge
 {
     const int64_t b = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t hub_blocks = (int64_t)P.hub_rows * P.hub_chunks;
+    const int64_t hub_blocks = P.hub_blocks;
     if (b < hub_blocks)
     {
-        advance_hub(g, (int32_t)(b / P.hub_chunks), (int)(b % P.hub_chunks), edge_shift, edge_op, pre, post);
+        if (P.hub_chunks == 0) advance_hub(g, (int32_t)b, 0, edge_shift, edge_op, pre, post); // vertex ops: the row stays whole
+        else
+        {
+            // no vertex ops: the hub rows' edges are the prefix [0, flat_edge0) of the adjacency array (ids are degree-sorted);
+            // CTA b walks edges [b, b + 1) * kHubChunk, which span at most three rows (each has >= 4096 edges)
+            const int64_t e0 = b * kHubChunk, e1 = e0 + kHubChunk < P.flat_edge0 ? e0 + kHubChunk : P.flat_edge0;
+            int32_t lo = 0, hi = P.hub_rows; // largest row with ptr[row] <= e0
+            while (hi - lo > 1)
+            {
+                const int32_t mid = lo + (hi - lo) / 2;
+                if (g.ptr[mid] <= e0) lo = mid;
+                else hi = mid;
+            }
+            for (int32_t row = lo; row < P.hub_rows; row++)
+            {
+                const int64_t rs = g.ptr[row], re = g.ptr[row + 1];
+                if (rs >= e1) break;
+                walk_row<kAdvThreads>(g, row, rs, rs > e0 ? rs : e0, re < e1 ? re : e1, threadIdx.x, lane, edge_shift, edge_op);
+            }
+        }
     }
     else if (b < hub_blocks + P.flat_blocks)
     {

@@ -33,11 +33,16 @@
 #define CC_UNROLL 4
 #define CC_BIG_CHUNK 8192
 
+// The label gathered a moment ago decides: if it is larger, the hook is issued as a fire-and-forget reduction (no return
+// value to wait for — four value-returning atomics per step were four serialised round trips) and the round counts as
+// "changed". That is conservative only when somebody else lowered the label in between; a round in which no gathered label
+// is larger issues no atomic at all, so the final, change-free round is still recognised.
 __device__ __forceinline__ void cc_hook_one(int32_t *__restrict__ comp, int32_t cs, int32_t dst, int32_t cd, bool &changed)
 {
     if (cs < cd)
     {
-        if (atomicMin(&comp[dst], cs) > cs) changed = true;
+        atomicMin(&comp[dst], cs);
+        changed = true;
     }
 }
 
@@ -51,25 +56,48 @@ cc_hook_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj,
     const unsigned FULL = 0xffffffffu;
     const uint64_t pol = l2_policy_evict_first();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int big_blocks = n_big * big_chunks;
+    // rows with >= 4096 edges: their edges are the prefix [0, ptr[n_big]) of the adjacency array (ids are degree-sorted), cut
+    // into CC_BIG_CHUNK-edge chunks, one CTA each; a chunk spans at most three such rows, found by a binary search over the
+    // row pointers. (One CTA per (row, chunk slot of the LONGEST row) launched ~10^6 CTAs with nothing to do at scale 24.)
+    const int big_blocks = big_chunks;
     if ((int)blockIdx.x < big_blocks)
     {
-        const int32_t row = blockIdx.x / big_chunks;
-        const int64_t s = ptr[row] + (int64_t)(blockIdx.x % big_chunks) * CC_BIG_CHUNK, e = min(ptr[row + 1], s + CC_BIG_CHUNK);
-        const int32_t cs = comp[col0 + row];
-        for (int64_t p0 = s + threadIdx.x; p0 < e; p0 += CC_THREADS * CC_UNROLL)
+        const int64_t hub_edges = ptr[n_big];
+        const int64_t e0 = (int64_t)blockIdx.x * CC_BIG_CHUNK, e1 = min(hub_edges, e0 + CC_BIG_CHUNK);
+        int32_t lo = 0, hi = n_big; // largest row with ptr[row] <= e0
+        while (hi - lo > 1)
         {
-            int32_t d[CC_UNROLL], cd[CC_UNROLL];
+            const int32_t mid = lo + (hi - lo) / 2;
+            if (ptr[mid] <= e0) lo = mid;
+            else hi = mid;
+        }
+        int32_t row = lo;
+        int64_t row_end = ptr[row + 1];
+        int32_t cs = comp[col0 + row];
+        for (int64_t p0 = e0 + threadIdx.x; p0 < e1; p0 += CC_THREADS * CC_UNROLL)
+        {
+            int32_t d[CC_UNROLL], cd[CC_UNROLL], csk[CC_UNROLL];
 #pragma unroll
             for (int k = 0; k < CC_UNROLL; k++)
             {
                 const int64_t p = p0 + (int64_t)k * CC_THREADS;
-                d[k] = p < e ? ld_stream_s32(adj + p, pol) : -1;
+                d[k] = -1;
+                if (p < e1)
+                {
+                    while (p >= row_end) // (positions only grow: at most two steps per chunk)
+                    {
+                        row++;
+                        row_end = ptr[row + 1];
+                        cs = comp[col0 + row];
+                    }
+                    d[k] = ld_stream_s32(adj + p, pol);
+                }
+                csk[k] = cs;
             }
 #pragma unroll
             for (int k = 0; k < CC_UNROLL; k++) cd[k] = d[k] >= 0 ? comp[d[k]] : INT_MIN;
 #pragma unroll
-            for (int k = 0; k < CC_UNROLL; k++) cc_hook_one(comp, cs, d[k], cd[k], changed);
+            for (int k = 0; k < CC_UNROLL; k++) cc_hook_one(comp, csk[k], d[k], cd[k], changed);
         }
         if (__syncthreads_or(changed) && threadIdx.x == 0) *changed_flag = 1;
         return;
@@ -123,9 +151,19 @@ cc_hook_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj,
 static int cc_launch_hook(vglb_ctx *ctx, const vglb_graph *g, int32_t *comp, int32_t col0, int *d_changed)
 {
     const int32_t n_big = g->tier_border[0], rows_with_edges = g->tier_border[VGLB_NUM_TIERS - 2];
-    const int big_chunks = (int)ceil_div64(g->max_degree > 0 ? g->max_degree : 1, CC_BIG_CHUNK);
+    if (g->cc_hub_edges_plus1 == 0) // edges of the rows with >= 4096 edges = row pointer at the first tier border, once per graph
+    {
+        int64_t e = 0;
+        if (n_big > 0)
+        {
+            CUDA_TRY(cudaMemcpyAsync(&e, g->d_out_ptr + n_big, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        }
+        ((vglb_graph *)g)->cc_hub_edges_plus1 = e + 1;
+    }
+    const int big_chunks = (int)ceil_div64(g->cc_hub_edges_plus1 - 1, CC_BIG_CHUNK);
     const int64_t warps = ceil_div64(rows_with_edges - n_big, 32);
-    const int64_t grid = (int64_t)n_big * big_chunks + ceil_div64(warps, CC_THREADS / 32);
+    const int64_t grid = (int64_t)big_chunks + ceil_div64(warps, CC_THREADS / 32);
     VGLB_REQUIRE(grid < 0x7fffffffLL, "vglb_cc: grid too large");
     if (grid > 0)
     {

@@ -306,7 +306,7 @@ __device__ __forceinline__ void sssp_relax_batch(uint32_t *__restrict__ dist, ui
     }
 #pragma unroll
     for (int k = 0; k < N; k++)
-        if (!(word[k] & bit[k])) atomicOr(word_ptr[k], bit[k]);
+        if (bit[k] && !(word[k] & bit[k])) atomicOr(word_ptr[k], bit[k]);
 }
 
 __global__ void __launch_bounds__(SSSP_THREADS)
