@@ -70,6 +70,7 @@ struct vglb_ctx
     unsigned long long *h_mailbox; // 64 words, word 63 = sequence number
     unsigned long long mailbox_seq;
     int pr_carveout_set;   // pr_sweep_kernel's shared-memory carve-out preference has been set on this device
+    int prb_smem_set;      // pr_bin_kernel's dynamic shared-memory limit has been raised on this device
 };
 
 struct vglb_graph
@@ -100,6 +101,8 @@ struct vglb_graph
     int32_t *d_pr_ve_adj;       // padded column-major copy of the rows with 1..31 edges (VectorExtension twin)
     int64_t *d_pr_ve_ptr;
     int32_t pr_ve_segments;
+    void *pr_bins;              // column-binned copy of the heavy rows (PrBins, pagerank_bins.cu); NULL = warp tasks
+    int pr_bins_tried;
     int32_t col_of_row0;        // column id of local row 0 (0 unless the graph is one rank's part of a partitioned graph)
     // 1D partition (partition.cu). On one GPU: cols = V_orig = vp = V, E_global = E, comm = NULL.
     // On a partitioned graph V / E are this rank's rows / edges; vertex state is indexed by COLUMN id in [0, cols):
@@ -173,6 +176,8 @@ void vglb_graph_set_unpartitioned(vglb_graph *g);
 int vglb_graph_derive_incoming(vglb_ctx *ctx, vglb_graph *g);
 int vglb_pr_build_tasks_host(vglb_ctx *ctx, vglb_graph *g, const int64_t *h_ptr, int32_t heavy_rows, int32_t long_rows);
 void vglb_graph_free_fields(vglb_graph *g);
+void vglb_pr_bins_free(vglb_graph *g);   // pagerank_bins.cu
+int vglb_pr_bins_wanted(const vglb_graph *g); // 1: the PageRank sweep of this graph uses the column-binned heavy rows
 
 // collectives on the context stream (partition.cu); asynchronous, every rank must make the same call
 enum { VGLB_DT_I32 = 0, VGLB_DT_U32 = 1, VGLB_DT_I64 = 2, VGLB_DT_F64 = 3 };

@@ -261,6 +261,7 @@ void vglb_graph_free_fields(vglb_graph *g)
     vglb_dev_free(g->d_in_ptr); vglb_dev_free(g->d_in_adj);
     vglb_dev_free(g->d_fwd); vglb_dev_free(g->d_bwd); vglb_dev_free(g->d_edge_order); vglb_dev_free(g->d_in_to_out_pos);
     vglb_dev_free(g->d_indeg_noloops); vglb_dev_free(g->d_pr_inv); vglb_dev_free(g->d_pr_contrib[0]); vglb_dev_free(g->d_pr_contrib[1]); vglb_dev_free(g->d_pr_dangling); vglb_dev_free(g->d_pr_tasks); vglb_dev_free(g->d_pr_piece_partial); vglb_dev_free(g->d_pr_piece_count); vglb_dev_free(g->d_pr_ve_adj); vglb_dev_free(g->d_pr_ve_ptr);
+    vglb_pr_bins_free(g);
     vglb_dev_free(g->d_visited); vglb_dev_free(g->d_front_bm[0]); vglb_dev_free(g->d_front_bm[1]);
     vglb_dev_free(g->d_queue[0]); vglb_dev_free(g->d_queue[1]); vglb_dev_free(g->d_scratch_i32);
 }
@@ -572,7 +573,7 @@ extern "C" int vglb_graph_from_csr(vglb_ctx *ctx, int32_t V, int64_t E, const in
     const unsigned vgrid = (unsigned)ceil_div64(V, 256);
     if (h_orig_to_sorted)
         BUILD_CUDA(cudaMemcpyAsync(g->d_fwd, h_orig_to_sorted, (size_t)V * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
-    if (chunks > 1)
+    if (chunks > 1 && !vglb_pr_bins_wanted(g))
     {
         // the host is idle while the DMA runs: PageRank's warp-task table of the rows with >= 32 edges (pagerank.cu) is built
         // from the caller's row pointers now instead of costing 3-4 ms later (rows are degree-sorted: binary search the borders)

@@ -277,6 +277,61 @@ __device__ __forceinline__ void pr_tail_segments(const PrParams &P, const L2Pol 
     }
 }
 
+// ---- heavy rows whose edges went through the column bins (pagerank_bins.cu): add up the row's partial sums ---------------------------
+// slot[class * nch + chunk]; a row with <= PRB_RC edges is one chunk (chunk = row + xc), the few longer ones have several.
+__device__ __forceinline__ void pr_finish_binned(const PrParams &P, const L2Pol &pol, int b, int warp, int lane, float dang, double &dang_local)
+{
+    if (b < P.bin_long_blocks)
+    {
+        const int32_t row = b * PR_WARPS + warp; // one warp per long row
+        if (row >= P.bin_long_rows) return;
+        const int32_t c0 = P.bin_rc_ptr[row], n = (P.bin_rc_ptr[row + 1] - c0) * P.bin_nc;
+        float acc = 0.f;
+        for (int i = lane; i < n; i += 32)
+        {
+            const int cls = i % P.bin_nc, ch = c0 + i / P.bin_nc;
+            acc += ld_stream_f32(P.bin_slot + (int64_t)cls * P.bin_nch + ch, pol.stream);
+        }
+        acc = warp_sum_f32(acc);
+        if (lane == 0) pr_epilogue(P, pol, row, acc, dang, dang_local);
+        return;
+    }
+    const int32_t row = P.bin_long_rows + (b - P.bin_long_blocks) * PR_THREADS + warp * 32 + lane;
+    if (row >= P.bin_rows) return;
+    const float *s = P.bin_slot + row + P.bin_xc;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    for (int c = 0; c < P.bin_nc; c += 12) // 12 independent loads in flight (33 classes: three rounds)
+    {
+        float x[12];
+#pragma unroll
+        for (int i = 0; i < 12; i++) x[i] = c + i < P.bin_nc ? ld_stream_f32(s + (int64_t)(c + i) * P.bin_nch, pol.stream) : 0.f;
+#pragma unroll
+        for (int i = 0; i < 12; i += 4)
+        {
+            acc0 += x[i];
+            acc1 += x[i + 1];
+            acc2 += x[i + 2];
+            acc3 += x[i + 3];
+        }
+    }
+    pr_epilogue(P, pol, row, (acc0 + acc1) + (acc2 + acc3), dang, dang_local);
+}
+
+// next sweep's dangling mass: fp64 block reduction, one atomic per CTA that has any
+__device__ __forceinline__ void pr_dangling_reduce(const PrParams &P, double *s_dang, double dang_local, int lane, int warp)
+{
+    dang_local = warp_sum_f64(dang_local);
+    if (lane == 0) s_dang[warp] = dang_local;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < PR_WARPS; w++) t += s_dang[w];
+        if (t != 0.0) atomicAdd(P.dangling_out, t);
+    }
+}
+
 __global__ void __launch_bounds__(PR_THREADS, PR_MIN_CTAS) pr_sweep_kernel(const __grid_constant__ PrParams P)
 {
     L2Pol pol;
@@ -311,20 +366,55 @@ __global__ void __launch_bounds__(PR_THREADS, PR_MIN_CTAS) pr_sweep_kernel(const
         // rows without out-edges: only the post-op, coalesced
         const int32_t row0 = P.zero_first + (b - P.heavy_blocks - P.tail_blocks) * PR_ZERO_ROWS_PER_CTA;
         const int32_t row1 = min(row0 + PR_ZERO_ROWS_PER_CTA, P.rows);
+        // every such row gets the same rank k + d * (0 + dangling) (pr_epilogue with sum = 0): one multiply and one store per row
+        const float rank0 = __fadd_rn(P.k, __fmul_rn(P.d, __fadd_rn(0.f, dang)));
+        int ndang = 0;
 #pragma unroll 4
-        for (int32_t row = row0 + threadIdx.x; row < row1; row += PR_THREADS) pr_epilogue(P, pol, row, 0.f, dang, dang_local);
+        for (int32_t row = row0 + threadIdx.x; row < row1; row += PR_THREADS)
+        {
+            const float inv_r = ld_stream_f32(P.inv + row, pol.stream);
+            if (inv_r != 0.0f)
+            {
+                const float c = __fmul_rn(rank0, inv_r);
+                st_stream_f32(P.contrib_out + row, c);
+                for (int p = 0; p < P.npeers; p++) st_stream_f32(P.peer_out[p] + row, c);
+            }
+            else
+                ndang++;
+            if (P.rank_out) st_stream_f32(P.rank_out + row, rank0);
+        }
+        // (n equal terms: every partial sum is an exact multiple of a 24-bit value, so n * term is what adding them one by one gives)
+        dang_local += (double)__fdiv_rn(rank0, P.v_as_float) * (double)ndang;
     }
-    // next sweep's dangling mass: fp64 block reduction, one atomic per CTA that has any
-    dang_local = warp_sum_f64(dang_local);
-    if (lane == 0) s_dang[warp] = dang_local;
-    __syncthreads();
-    if (threadIdx.x == 0)
-    {
-        double t = 0.0;
-#pragma unroll
-        for (int w = 0; w < PR_WARPS; w++) t += s_dang[w];
-        if (t != 0.0) atomicAdd(P.dangling_out, t);
-    }
+    pr_dangling_reduce(P, s_dang, dang_local, lane, warp);
+}
+
+// the cold bin of the column-binned heavy rows: PR_COLD_SPU steps per warp (columns beyond the shared-memory bins, gathered from global
+// memory — in a kernel of its own: it needs the L1 that pr_bin_kernel gives to shared memory, and pr_sweep_kernel must not carry
+// its 4 KB of staging: every KB of shared memory there costs L1 hits of the tail rows)
+__global__ void __launch_bounds__(PR_THREADS, PR_MIN_CTAS) pr_cold_bin_kernel(const __grid_constant__ PrParams P)
+{
+    L2Pol pol;
+    pol.stream = l2_policy_evict_first();
+    pol.keep = l2_policy_evict_last();
+    __shared__ float s_stage[PR_WARPS][2 * PRB_STAGE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int end_step = P.bin_nkchunks * PRB_SPC;
+    const int u = (P.bins.cold_chunk0 * PRB_SPC) / PR_COLD_SPU + blockIdx.x * PR_WARPS + warp; // units of PR_COLD_SPU steps
+    if (u * PR_COLD_SPU < end_step) prb_unit<true>(P.bins, pol, NULL, u * PR_COLD_SPU, (u + 1) * PR_COLD_SPU, end_step, lane, s_stage[warp]);
+}
+
+__global__ void __launch_bounds__(PR_THREADS) pr_finish_kernel(const __grid_constant__ PrParams P)
+{
+    L2Pol pol;
+    pol.stream = l2_policy_evict_first();
+    pol.keep = l2_policy_evict_last();
+    __shared__ double s_dang[PR_WARPS];
+    const float dang = (float)(*P.dangling_in);
+    double dang_local = 0.0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pr_finish_binned(P, pol, blockIdx.x, warp, lane, dang, dang_local);
+    pr_dangling_reduce(P, s_dang, dang_local, lane, warp);
 }
 
 // inv[v] = (float)(1.0 / indeg_noloops[v]) or 0 — pr.hpp:66-73 (double division then narrowing, like the reference)
@@ -573,6 +663,9 @@ static double pr_now()
     return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
+// the column-binned heavy rows are used on one GPU (a partitioned graph keeps the warp tasks); VGLB_PR_NO_BINS = developer A/B knob
+int vglb_pr_bins_wanted(const vglb_graph *g) { return !g->comm && g->part_world <= 1 && getenv("VGLB_PR_NO_BINS") == NULL; }
+
 int vglb_pr_prepare(vglb_ctx *ctx, vglb_graph *g, int iters)
 {
     const bool trace = getenv("VGLB_PR_TRACE") != NULL; // developer aid: time of every one-off preparation stage
@@ -628,7 +721,14 @@ int vglb_pr_prepare(vglb_ctx *ctx, vglb_graph *g, int iters)
         vglb_dev_free(d_indeg);
     }
     lap("inverse in-degrees");
-    if (!g->d_pr_piece_count)
+    if (vglb_pr_bins_wanted(g) && !g->pr_bins_tried)
+    {
+        g->pr_bins_tried = 1;
+        int rc = vglb_pr_bins_build(ctx, g);
+        if (rc != VGLB_OK) return rc;
+        lap("column bins of the heavy rows");
+    }
+    if (!g->d_pr_piece_count && !g->pr_bins)
     {
         int rc = pr_build_tasks(ctx, g);
         if (rc != VGLB_OK) return rc;
@@ -661,6 +761,23 @@ int64_t vglb_pr_plan(const vglb_graph *g, int32_t rows, PrParams *P)
     P->piece_partial = g->d_pr_piece_partial;
     P->piece_count = g->d_pr_piece_count;
     P->heavy_blocks = (int32_t)ceil_div64(g->pr_ntasks, PR_WARPS);
+    if (const PrBins *B = (const PrBins *)g->pr_bins)
+    {
+        P->bin_slot = B->d_slot;
+        P->bin_rc_ptr = B->d_rc_ptr;
+        P->bin_nc = B->nb + 1;
+        P->bin_nch = B->nch;
+        P->bin_xc = B->xc;
+        P->bin_long_rows = B->long_rows;
+        P->bin_rows = B->rows;
+        P->bin_long_blocks = (int32_t)ceil_div64(B->long_rows, PR_WARPS);
+        P->bin_finish_blocks = P->bin_long_blocks + (int32_t)ceil_div64(B->rows - B->long_rows, PR_THREADS);
+        P->bin_nkchunks = B->nkchunks;
+        vglb_pr_bins_params(g, NULL, &P->bins);
+        P->bin_cold_blocks = (int32_t)ceil_div64((int64_t)(B->nkchunks - B->cold_chunk0) * PRB_SPC / PR_COLD_SPU, PR_WARPS);
+        P->ntasks = 0;
+        P->heavy_blocks = 0;
+    }
     P->ve_adj = g->d_pr_ve_adj;
     P->ve_ptr = g->d_pr_ve_ptr;
     P->ve_segments = g->pr_ve_segments;
@@ -689,6 +806,7 @@ int vglb_pr_launch_sweep(vglb_ctx *ctx, const PrParams &P, int64_t nblocks)
     if (!ctx->pr_carveout_set)
     {
         CUDA_TRY(cudaFuncSetAttribute(pr_sweep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
+        CUDA_TRY(cudaFuncSetAttribute(pr_cold_bin_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
         ctx->pr_carveout_set = 1;
     }
     pr_sweep_kernel<<<(unsigned)nblocks, PR_THREADS, 0, ctx->stream>>>(P);
@@ -809,8 +927,26 @@ extern "C" int vglb_pagerank_ex(vglb_ctx *ctx, vglb_graph *g, int iters, float d
         if (p2p && it < iters - 1)
             for (int p = 0; p < g->part_world; p++)
                 if (p != g->part_rank) P.peer_out[P.npeers++] = g->d_pr_peer[(it + 1) & 1][p] + col0;
-        rc = vglb_pr_launch_sweep(ctx, P, nblocks);
+        if (g->pr_bins)
+        {
+            rc = vglb_pr_bins_launch(ctx, g, P.contrib_in); // partial sums of the heavy rows: the shared-memory bins
+            if (rc != VGLB_OK) return rc;
+            P.bins.contrib_in = P.contrib_in;
+        }
+        if (g->pr_bins && P.bin_cold_blocks > 0)
+        {
+            pr_cold_bin_kernel<<<(unsigned)P.bin_cold_blocks, PR_THREADS, 0, ctx->stream>>>(P); // their cold bin
+            KERNEL_TRY();
+            ctx->launches++;
+        }
+        rc = vglb_pr_launch_sweep(ctx, P, nblocks); // the rows with < 32 edges (all rows without the bins)
         if (rc != VGLB_OK) return rc;
+        if (g->pr_bins && P.bin_finish_blocks > 0)
+        {
+            pr_finish_kernel<<<(unsigned)P.bin_finish_blocks, PR_THREADS, 0, ctx->stream>>>(P);
+            KERNEL_TRY();
+            ctx->launches++;
+        }
         if (ref_order && it < iters - 1)
         {
             rc = reference_dangling(it + 1); // replaces the fp64 sum the sweep's epilogue accumulated
