@@ -89,7 +89,12 @@ int vglb_graph_from_edges(vglb_ctx *ctx, int32_t vertices, int64_t edges, const 
  * sorted numbering: get_vertex_pointers()/get_adjacent_ids(), vect_csr_graph.h:99-100) and copy it to HBM.
  * h_orig_to_sorted (forward_conversion) may be NULL (identity). Incoming arrays may be NULL. The upload is pipelined
  * (pinned host memory recommended): the adjacency goes up in chunks on a second stream while the in-degrees without self
- * loops are counted behind it and PageRank's warp-task table is built on the host. All copies have completed on return. */
+ * loops are counted behind it. All copies have completed on return.
+ * vglb_set_upload_hint(ctx, VGLB_HINT_PAGERANK): the caller will run PageRank on the graphs it uploads next, so everything the
+ * sweep needs beyond the CSR (pr.hpp:28-73 and the column-binned copy of the rows with >= 32 edges, csrc/pagerank_bins.cu) is
+ * built behind the upload as well instead of inside the first vglb_pagerank call. 0 clears the hint. */
+#define VGLB_HINT_PAGERANK 1
+int vglb_set_upload_hint(vglb_ctx *ctx, int hints);
 int vglb_graph_from_csr(vglb_ctx *ctx, int32_t vertices, int64_t edges, const int64_t *h_out_ptr,
                         const int32_t *h_out_adj, const int32_t *h_orig_to_sorted, const int64_t *h_in_ptr,
                         const int32_t *h_in_adj, vglb_graph **out_graph);

@@ -28,6 +28,7 @@ _LIB = None
 GEN_RMAT, GEN_KRONECKER, GEN_UNIFORM = 0, 1, 2
 SCATTER, GATHER, ORIGINAL = 0, 1, 2
 GRAPH_WITH_INCOMING, GRAPH_WITH_EDGE_ORDER = 1, 2
+HINT_PAGERANK = 1  # vglb_set_upload_hint
 MASTER_SEED = 0xB200
 NUM_TIERS = 8
 
@@ -89,6 +90,7 @@ _SIGNATURES = {
     "vglb_generate_edges_device": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, C.c_uint64, C.c_int, C.c_int, C.c_int, _P, _P]),
     "vglb_generate_edges_host": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_uint64, C.c_int, C.c_int, C.c_int, _P, _P]),
     "vglb_graph_from_edges": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, C.c_int, C.c_int, C.POINTER(_P)]),
+    "vglb_set_upload_hint": (C.c_int, [_P, C.c_int]),
     "vglb_graph_from_csr": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(_P)]),
     "vglb_graph_free": (C.c_int, [_P, _P]),
     "vglb_el_container_save": (C.c_int, [C.c_char_p, C.c_int32, C.c_int64, _P, _P]),

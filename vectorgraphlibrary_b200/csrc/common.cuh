@@ -70,6 +70,7 @@ struct vglb_ctx
     unsigned long long *h_mailbox; // 64 words, word 63 = sequence number
     unsigned long long mailbox_seq;
     int pr_carveout_set;   // pr_sweep_kernel's shared-memory carve-out preference has been set on this device
+    int upload_hint;       // VGLB_HINT_* (vglb_set_upload_hint)
     int prb_smem_set;      // pr_bin_kernel's dynamic shared-memory limit has been raised on this device
 };
 
@@ -177,6 +178,7 @@ int vglb_graph_derive_incoming(vglb_ctx *ctx, vglb_graph *g);
 int vglb_pr_build_tasks_host(vglb_ctx *ctx, vglb_graph *g, const int64_t *h_ptr, int32_t heavy_rows, int32_t long_rows);
 void vglb_graph_free_fields(vglb_graph *g);
 void vglb_pr_bins_free(vglb_graph *g);   // pagerank_bins.cu
+int vglb_pr_bins_build_rows(vglb_ctx *ctx, vglb_graph *g, int32_t rows); // rows = ids with >= 32 edges (tier_border[1])
 int vglb_pr_bins_wanted(const vglb_graph *g); // 1: the PageRank sweep of this graph uses the column-binned heavy rows
 
 // collectives on the context stream (partition.cu); asynchronous, every rank must make the same call

@@ -485,6 +485,13 @@ extern "C" int vglb_graph_from_edges(vglb_ctx *ctx, int32_t V, int64_t E, const 
     return VGLB_OK;
 }
 
+extern "C" int vglb_set_upload_hint(vglb_ctx *ctx, int hints)
+{
+    VGLB_REQUIRE(ctx != NULL && (hints & ~VGLB_HINT_PAGERANK) == 0, "vglb_set_upload_hint: bad argument");
+    ctx->upload_hint = hints;
+    return VGLB_OK;
+}
+
 extern "C" int vglb_graph_from_csr(vglb_ctx *ctx, int32_t V, int64_t E, const int64_t *h_out_ptr,
                                    const int32_t *h_out_adj, const int32_t *h_orig_to_sorted, const int64_t *h_in_ptr,
                                    const int32_t *h_in_adj, vglb_graph **out_graph)
@@ -523,24 +530,58 @@ extern "C" int vglb_graph_from_csr(vglb_ctx *ctx, int32_t V, int64_t E, const in
     BUILD_CUDA(cudaEventRecord(ctx->ev_chunk[0], ctx->stream));
     BUILD_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[0], 0)); // (orders the copy stream after earlier work on the buffers)
     const int chunks = E >= (1 << 22) ? 8 : 1;
-    int32_t row0 = 0;
+    // rows are degree-sorted: binary search the first row with fewer than d edges
+    auto rows_with_degree_at_least = [&](int64_t d) {
+        int32_t lo = 0, hi = V;
+        while (lo < hi)
+        {
+            const int32_t mid = lo + (hi - lo) / 2;
+            if (h_out_ptr[mid + 1] - h_out_ptr[mid] >= d) lo = mid + 1;
+            else hi = mid;
+        }
+        return lo;
+    };
+    // chunk k = rows [border[k], border[k+1]): border[k] = first row whose edges start at or after the k-th eighth of the edge array
+    int32_t border[9];
+    border[0] = 0;
+    for (int k = 1; k < chunks; k++)
+    {
+        const int64_t target = E / chunks * k;
+        int32_t lo = border[k - 1], hi = V;
+        while (lo < hi)
+        {
+            const int32_t mid = lo + (hi - lo) / 2;
+            if (h_out_ptr[mid] < target) lo = mid + 1;
+            else hi = mid;
+        }
+        border[k] = lo;
+    }
+    border[chunks] = V;
+    // PageRank's column-binned copy of the rows with >= 32 edges (pagerank_bins.cu) only needs those rows: when the caller's
+    // buffer is pinned (every copy can be queued at once) it is built as soon as their last chunk has landed, behind the rest of
+    // the upload. The border nearest to the end of those rows is moved there.
+    int heavy_chunk = -1; // chunk that ends the heavy rows
+    int32_t heavy_rows = 0;
+    if (chunks > 1 && (ctx->upload_hint & VGLB_HINT_PAGERANK) && vglb_pr_bins_wanted(g))
+    {
+        cudaPointerAttributes attr;
+        const bool pinned = cudaPointerGetAttributes(&attr, h_out_adj) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        heavy_rows = rows_with_degree_at_least(vglb_tier_degree(1));
+        if (pinned && heavy_rows > 0 && heavy_rows < V && h_out_ptr[heavy_rows] >= 0 && h_out_ptr[heavy_rows] <= E)
+        {
+            int best = 1;
+            for (int k = 2; k < chunks; k++)
+                if (llabs(h_out_ptr[border[k]] - h_out_ptr[heavy_rows]) < llabs(h_out_ptr[border[best]] - h_out_ptr[heavy_rows])) best = k;
+            border[best] = heavy_rows;
+            for (int k = best - 1; k > 0; k--) border[k] = std::min(border[k], heavy_rows);
+            for (int k = best + 1; k < chunks; k++) border[k] = std::max(border[k], heavy_rows);
+            heavy_chunk = best - 1;
+        }
+    }
     for (int k = 0; k < chunks; k++)
     {
-        // first row whose edges start at or after the k+1-th eighth of the edge array
-        int32_t row1 = V;
-        if (k + 1 < chunks)
-        {
-            const int64_t target = E / chunks * (k + 1);
-            int32_t lo = row0, hi = V;
-            while (lo < hi)
-            {
-                const int32_t mid = lo + (hi - lo) / 2;
-                if (h_out_ptr[mid] < target) lo = mid + 1;
-                else hi = mid;
-            }
-            row1 = lo;
-        }
-        const int64_t e0 = h_out_ptr[row0], e1 = h_out_ptr[row1];
+        const int64_t e0 = h_out_ptr[border[k]], e1 = h_out_ptr[border[k + 1]];
         if (e0 < 0 || e1 < e0 || e1 > E)
         {
             cudaStreamSynchronize(ctx->copy_stream);
@@ -549,17 +590,44 @@ extern "C" int vglb_graph_from_csr(vglb_ctx *ctx, int32_t V, int64_t E, const in
             cleanup();
             return VGLB_EINVAL;
         }
+    }
+    if (heavy_chunk >= 0) // pinned source: queue every copy first
+        for (int k = 0; k < chunks; k++)
+        {
+            const int64_t e0 = h_out_ptr[border[k]], e1 = h_out_ptr[border[k + 1]];
+            if (e1 > e0)
+                BUILD_CUDA(cudaMemcpyAsync(g->d_out_adj + e0, h_out_adj + e0, (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+            BUILD_CUDA(cudaEventRecord(ctx->ev_chunk[k], ctx->copy_stream));
+        }
+    for (int k = 0; k < chunks; k++)
+    {
+        const int32_t row0 = border[k], row1 = border[k + 1];
+        const int64_t e0 = h_out_ptr[row0], e1 = h_out_ptr[row1];
         if (e1 > e0)
         {
-            BUILD_CUDA(cudaMemcpyAsync(g->d_out_adj + e0, h_out_adj + e0, (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
-            BUILD_CUDA(cudaEventRecord(ctx->ev_chunk[k], ctx->copy_stream));
+            if (heavy_chunk < 0)
+            {
+                BUILD_CUDA(cudaMemcpyAsync(g->d_out_adj + e0, h_out_adj + e0, (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+                BUILD_CUDA(cudaEventRecord(ctx->ev_chunk[k], ctx->copy_stream));
+            }
             BUILD_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[k], 0));
             indegree_noloops_rows_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(g->d_out_ptr, g->d_out_adj, row0, row1, e0, e1, V,
                                                                                      g->d_indeg_noloops, d_bad);
             BUILD_CUDA(cudaGetLastError());
             ctx->launches++;
         }
-        row0 = row1;
+        if (k == heavy_chunk)
+        {
+            // (the row pointers were checked by csr_ptr_check_kernel: a bad array fails the call below, not the build)
+            int bad = 0;
+            BUILD_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            BUILD_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (!bad)
+            {
+                g->pr_bins_tried = 1;
+                BUILD_TRY(vglb_pr_bins_build_rows(ctx, g, heavy_rows));
+            }
+        }
     }
     if (h_in_ptr)
     {
@@ -576,17 +644,7 @@ extern "C" int vglb_graph_from_csr(vglb_ctx *ctx, int32_t V, int64_t E, const in
     if (chunks > 1 && !vglb_pr_bins_wanted(g))
     {
         // the host is idle while the DMA runs: PageRank's warp-task table of the rows with >= 32 edges (pagerank.cu) is built
-        // from the caller's row pointers now instead of costing 3-4 ms later (rows are degree-sorted: binary search the borders)
-        auto rows_with_degree_at_least = [&](int64_t d) {
-            int32_t lo = 0, hi = V;
-            while (lo < hi)
-            {
-                const int32_t mid = lo + (hi - lo) / 2;
-                if (h_out_ptr[mid + 1] - h_out_ptr[mid] >= d) lo = mid + 1;
-                else hi = mid;
-            }
-            return lo;
-        };
+        // from the caller's row pointers now instead of costing 3-4 ms later
         BUILD_TRY(vglb_pr_build_tasks_host(ctx, g, h_out_ptr, rows_with_degree_at_least(vglb_tier_degree(1)),
                                            rows_with_degree_at_least(vglb_tier_degree(0))));
     }

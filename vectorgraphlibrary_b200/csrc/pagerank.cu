@@ -332,7 +332,10 @@ __device__ __forceinline__ void pr_dangling_reduce(const PrParams &P, double *s_
     }
 }
 
-__global__ void __launch_bounds__(PR_THREADS, PR_MIN_CTAS) pr_sweep_kernel(const __grid_constant__ PrParams P)
+// HEAVY = false: the graph's heavy rows went through the column bins — only tail and zero-row blocks, so the kernel needs fewer
+// registers and more CTAs fit an SM (the tail rows are latency-bound).
+template <bool HEAVY>
+__global__ void __launch_bounds__(PR_THREADS, HEAVY ? PR_MIN_CTAS : PR_TAIL_MIN_CTAS) pr_sweep_kernel(const __grid_constant__ PrParams P)
 {
     L2Pol pol;
     pol.stream = l2_policy_evict_first();
@@ -351,7 +354,7 @@ __global__ void __launch_bounds__(PR_THREADS, PR_MIN_CTAS) pr_sweep_kernel(const
     double dang_local = 0.0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    if (b < P.heavy_blocks)
+    if (HEAVY && b < P.heavy_blocks)
     {
         const int t = b * PR_WARPS + warp;
         if (t < P.ntasks) pr_heavy_task(P, pol, P.tasks[t], lane, dang, dang_local);
@@ -805,11 +808,13 @@ int vglb_pr_launch_sweep(vglb_ctx *ctx, const PrParams &P, int64_t nblocks)
     // (a function attribute is per device: remembered per context, not per process)
     if (!ctx->pr_carveout_set)
     {
-        CUDA_TRY(cudaFuncSetAttribute(pr_sweep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
+        CUDA_TRY(cudaFuncSetAttribute(pr_sweep_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
+        CUDA_TRY(cudaFuncSetAttribute(pr_sweep_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
         CUDA_TRY(cudaFuncSetAttribute(pr_cold_bin_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
         ctx->pr_carveout_set = 1;
     }
-    pr_sweep_kernel<<<(unsigned)nblocks, PR_THREADS, 0, ctx->stream>>>(P);
+    if (P.heavy_blocks > 0) pr_sweep_kernel<true><<<(unsigned)nblocks, PR_THREADS, 0, ctx->stream>>>(P);
+    else pr_sweep_kernel<false><<<(unsigned)nblocks, PR_THREADS, 0, ctx->stream>>>(P);
     KERNEL_TRY();
     ctx->launches++;
     return VGLB_OK;

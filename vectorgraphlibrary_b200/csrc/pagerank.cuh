@@ -20,13 +20,18 @@
 #ifndef PR_MIN_CTAS
 #define PR_MIN_CTAS 5             // __launch_bounds__ minimum resident CTAs per SM (48 registers)
 #endif
+#ifndef PR_TAIL_MIN_CTAS
+#define PR_TAIL_MIN_CTAS 8        // the same for the sweep kernel without heavy blocks (32 registers)
+#endif
 #ifndef PR_VE_SEGS_PER_WARP
-#define PR_VE_SEGS_PER_WARP 16    // 32-row segments of the padded tail copy handled by one warp
+#define PR_VE_SEGS_PER_WARP 8     // 32-row segments of the padded tail copy handled by one warp (r2 A/B with the column bins: 16 -> 0.611, 8 -> 0.527 ms)
 #endif
 #ifndef PR_COLD_SPU
 #define PR_COLD_SPU 8            // steps of the cold bin handled by one warp of pr_cold_bin_kernel (1: 212 us, 8: 137 us at RMAT-24)
 #endif
+#ifndef PR_ZERO_ROWS_PER_CTA
 #define PR_ZERO_ROWS_PER_CTA 4096 // rows without out-edges handled by one CTA
+#endif
 
 // a warp's unit of work in the heavy region (rows with degree >= 32)
 struct PrTask

@@ -368,9 +368,11 @@ static int prb_exclusive_sum(vglb_ctx *ctx, const T *in, T *out, int64_t n, bool
 
 // Builds the binned copy of the heavy rows (degree >= 32) of a one-GPU graph. Leaves g->pr_bins NULL when there is nothing to
 // bin (no heavy rows).
-int vglb_pr_bins_build(vglb_ctx *ctx, vglb_graph *g)
+int vglb_pr_bins_build(vglb_ctx *ctx, vglb_graph *g) { return vglb_pr_bins_build_rows(ctx, g, g->tier_border[1]); }
+
+// (vglb_graph_from_csr calls this before the graph is complete: only V, d_out_ptr and the adjacency of rows [0, rows) are used)
+int vglb_pr_bins_build_rows(vglb_ctx *ctx, vglb_graph *g, int32_t rows)
 {
-    const int32_t rows = g->tier_border[1];
     if (rows <= 0 || g->comm) return VGLB_OK;
     cudaStream_t st = ctx->stream;
     int32_t long_rows = 0;
