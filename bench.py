@@ -72,7 +72,7 @@ def ncu_traffic(workload: str, world: int):
     same command (profiles/, B200_PROFILING.md recipe); None where no capture of the configuration exists."""
     if world != 1:
         return None
-    names = {"pr": ["r2_pr_sweep_ncu_full.txt", "r1_pr_sweep_ncu_full.txt"]}.get(workload, [])
+    names = {"pr": ["r2_pr_sweep_ncu_full.txt"]}.get(workload, [])  # (first line of that kind = the four kernels of a sweep together)
     for name in names:
         try:
             for line in open(os.path.join(ROOT, "profiles", name)):

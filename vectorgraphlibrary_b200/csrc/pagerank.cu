@@ -666,8 +666,13 @@ static double pr_now()
     return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
-// the column-binned heavy rows are used on one GPU (a partitioned graph keeps the warp tasks); VGLB_PR_NO_BINS = developer A/B knob
-int vglb_pr_bins_wanted(const vglb_graph *g) { return !g->comm && g->part_world <= 1 && getenv("VGLB_PR_NO_BINS") == NULL; }
+// the column-binned heavy rows (pagerank_bins.cu); VGLB_PR_NO_BINS = developer A/B knob: warp tasks instead
+int vglb_pr_bins_wanted(const vglb_graph *g)
+{
+    // (PRB_H = 3 * 2^14 must be a multiple of the rank count: a bin then starts at owner 0 of a local row)
+    if (g->comm && (g->part_world > 8 || PRB_H % g->part_world != 0)) return 0;
+    return getenv("VGLB_PR_NO_BINS") == NULL;
+}
 
 int vglb_pr_prepare(vglb_ctx *ctx, vglb_graph *g, int iters)
 {

@@ -82,7 +82,9 @@ struct PrbBinParams
     const int32_t *step_run0, *run_slot, *bin_chunk0, *cta_chunk0;
     const float *contrib_in;
     float *slot;
-    int32_t nb, cold_chunk0, cols, nruns;
+    int32_t nb, cold_chunk0, nruns;
+    int64_t cols;      // columns of the gathered vector (sorted ids 0 .. cols-1)
+    int32_t world, vp; // partitioned graph: column = owner * vp + local row, sorted id = local row * world + owner
     long long *cta_ns; // developer trace: time of every CTA (NULL = off)
 };
 

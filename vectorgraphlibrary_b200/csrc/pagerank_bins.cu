@@ -37,10 +37,15 @@
 //   bits 12..16 segmented-scan mask: add lane - 2^k in round k
 //   bit 17      some lane before this one has a start        bits 18..25 run starts in the whole step
 
-__device__ __forceinline__ int prb_class(int32_t v, int32_t row, int nb)
+// Bins are ranges of the SORTED (hottest first) vertex ids. On one GPU a column id is the sorted id; on one rank's part of a
+// partitioned graph column = owner * vp + local row and the sorted id is local row * ranks + owner (partition.cu).
+__device__ __forceinline__ uint32_t prb_sorted_id(int32_t v, int world, uint32_t vp)
 {
-    if (v == row) return PRB_DROP;
-    const int c = (int)((uint32_t)v / (uint32_t)PRB_H);
+    return world <= 1 ? (uint32_t)v : ((uint32_t)v % vp) * (uint32_t)world + (uint32_t)v / vp;
+}
+__device__ __forceinline__ int prb_class(uint32_t sorted_id, int nb)
+{
+    const int c = (int)(sorted_id / (uint32_t)PRB_H);
     return c < nb ? c : nb;
 }
 
@@ -94,8 +99,9 @@ __device__ __forceinline__ void prb_chunk_range(const int64_t *__restrict__ ptr,
 template <bool FILL>
 __global__ void __launch_bounds__(256) prb_scatter_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj,
                                                            const int32_t *__restrict__ rc_ptr, int32_t long_rows, int32_t xc, int32_t nch,
-                                                           int nb, int32_t *__restrict__ cnt, const int64_t *__restrict__ run_pos,
-                                                           int64_t w_smem, uint16_t *__restrict__ wcol, int32_t *__restrict__ cold)
+                                                           int nb, int32_t col_of_row0, int world, uint32_t vp, int32_t *__restrict__ cnt,
+                                                           const int64_t *__restrict__ run_pos, int64_t w_smem, uint16_t *__restrict__ wcol,
+                                                           int32_t *__restrict__ cold)
 {
     __shared__ long long s_acc[8][PRB_MAX_CLASSES];
     const unsigned FULL = 0xffffffffu;
@@ -110,8 +116,10 @@ __global__ void __launch_bounds__(256) prb_scatter_kernel(const int64_t *__restr
     for (int64_t p0 = e0; p0 < e1; p0 += 32)
     {
         const int64_t p = p0 + lane;
-        const int32_t v = p < e1 ? adj[p] : row;
-        const int c = prb_class(v, row, nb);
+        const int32_t self = col_of_row0 + row;
+        const int32_t v = p < e1 ? adj[p] : self;
+        const uint32_t sid = prb_sorted_id(v, world, vp);
+        const int c = v == self ? PRB_DROP : prb_class(sid, nb);
         const unsigned peers = __match_any_sync(FULL, c);
         const int rank = __popc(peers & ((1u << lane) - 1u));
         if (c != PRB_DROP)
@@ -119,7 +127,7 @@ __global__ void __launch_bounds__(256) prb_scatter_kernel(const int64_t *__restr
             if (FILL)
             {
                 const int64_t q = s_acc[warp][c] + rank;
-                if (c < nb) wcol[prb_phys16(q)] = (uint16_t)(v - c * PRB_H);
+                if (c < nb) wcol[prb_phys16(q)] = (uint16_t)(sid - (uint32_t)c * PRB_H);
                 else cold[prb_phys32(q - w_smem)] = v;
             }
         }
@@ -373,12 +381,14 @@ int vglb_pr_bins_build(vglb_ctx *ctx, vglb_graph *g) { return vglb_pr_bins_build
 // (vglb_graph_from_csr calls this before the graph is complete: only V, d_out_ptr and the adjacency of rows [0, rows) are used)
 int vglb_pr_bins_build_rows(vglb_ctx *ctx, vglb_graph *g, int32_t rows)
 {
-    if (rows <= 0 || g->comm) return VGLB_OK;
+    if (rows <= 0) return VGLB_OK;
+    const int world = g->comm ? g->part_world : 1;
+    const int64_t ncols = g->comm ? g->cols : (int64_t)g->V;
     cudaStream_t st = ctx->stream;
     int32_t long_rows = 0;
     int rc = vglb_graph_threshold_vertex(ctx, g, PRB_RC + 1, &long_rows); // rows with more than one chunk
     if (rc != VGLB_OK) return rc;
-    const int nb = (int)std::min<int64_t>(PRB_MAX_BINS, ceil_div64(g->V, PRB_H));
+    const int nb = (int)std::min<int64_t>(PRB_MAX_BINS, ceil_div64(ncols, PRB_H));
     const int nc = nb + 1;
 
     PrBins *B = (PrBins *)calloc(1, sizeof(PrBins));
@@ -411,8 +421,8 @@ int vglb_pr_bins_build_rows(vglb_ctx *ctx, vglb_graph *g, int32_t rows)
     if (n >= 0x7fffffffLL) { cleanup(); vglb_set_error("vglb_pr_bins_build: too many runs"); return VGLB_EINVAL; }
     // counts per (class, row chunk), scans, layout
     PRB_CUDA(vglb_dev_alloc(&d_cnt, (size_t)n * 4));
-    prb_scatter_kernel<false><<<(unsigned)ceil_div64(nch, 8), 256, 0, st>>>(g->d_out_ptr, g->d_out_adj, B->d_rc_ptr, long_rows, xc, nch, nb, d_cnt,
-                                                                           NULL, 0, NULL, NULL);
+    prb_scatter_kernel<false><<<(unsigned)ceil_div64(nch, 8), 256, 0, st>>>(g->d_out_ptr, g->d_out_adj, B->d_rc_ptr, long_rows, xc, nch, nb,
+                                                                           g->col_of_row0, world, (uint32_t)g->vp, d_cnt, NULL, 0, NULL, NULL);
     PRB_CUDA(cudaGetLastError());
     PRB_CUDA(vglb_dev_alloc(&d_plen, ((size_t)n + 1) * 8));
     PRB_CUDA(vglb_dev_alloc(&d_pflag, ((size_t)n + 1) * 4));
@@ -462,8 +472,9 @@ int vglb_pr_bins_build_rows(vglb_ctx *ctx, vglb_graph *g, int32_t rows)
     PRB_CUDA(vglb_dev_alloc(&d_run_pos, (size_t)n * 8));
     prb_run_pos_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(d_pos_scan, d_bin_start, nch, nc, d_run_pos);
     PRB_CUDA(cudaGetLastError());
-    prb_scatter_kernel<true><<<(unsigned)ceil_div64(nch, 8), 256, 0, st>>>(g->d_out_ptr, g->d_out_adj, B->d_rc_ptr, long_rows, xc, nch, nb, NULL,
-                                                                          d_run_pos, w_smem, B->d_wcol, B->d_cold);
+    prb_scatter_kernel<true><<<(unsigned)ceil_div64(nch, 8), 256, 0, st>>>(g->d_out_ptr, g->d_out_adj, B->d_rc_ptr, long_rows, xc, nch, nb,
+                                                                          g->col_of_row0, world, (uint32_t)g->vp, NULL, d_run_pos, w_smem, B->d_wcol,
+                                                                          B->d_cold);
     PRB_CUDA(cudaGetLastError());
     // run starts, slots, per-lane metadata, run numbers of the steps
     prb_runs_kernel<<<(unsigned)ceil_div64(n + nc, 256), 256, 0, st>>>(d_cnt, d_run_pos, d_pos_scan, d_flag_scan, d_bin_start, nch, nc,
@@ -522,11 +533,24 @@ __global__ void __launch_bounds__(PRB_THREADS, 1) pr_bin_kernel(const __grid_con
             __syncthreads();
             // this bin's slice of the contribution vector (the last bin of a small graph is shorter)
             const int64_t c0 = (int64_t)bin * PRB_H;
-            const int n = (int)min((int64_t)PRB_H, (int64_t)P.cols - c0);
-            const float4 *src = reinterpret_cast<const float4 *>(P.contrib_in + c0);
-            float4 *dst = reinterpret_cast<float4 *>(prb_smem);
-            for (int i = threadIdx.x; i < (n >> 2); i += PRB_THREADS) dst[i] = src[i];
-            for (int i = (n & ~3) + threadIdx.x; i < n; i += PRB_THREADS) prb_smem[i] = P.contrib_in[c0 + i];
+            const int n = (int)min((int64_t)PRB_H, P.cols - c0);
+            if (P.world <= 1)
+            {
+                const float4 *src = reinterpret_cast<const float4 *>(P.contrib_in + c0);
+                float4 *dst = reinterpret_cast<float4 *>(prb_smem);
+                for (int i = threadIdx.x; i < (n >> 2); i += PRB_THREADS) dst[i] = src[i];
+                for (int i = (n & ~3) + threadIdx.x; i < n; i += PRB_THREADS) prb_smem[i] = P.contrib_in[c0 + i];
+            }
+            else
+            {
+                // sorted id c0 + i = local row * ranks + owner lives in column owner * vp + local row: one coalesced stream per owner
+                // (PRB_H is a multiple of every supported rank count, so a bin starts at owner 0)
+                const int per_owner = (n + P.world - 1) / P.world;
+                const int64_t l0 = c0 / P.world;
+                for (int o = 0; o < P.world; o++)
+                    for (int l = threadIdx.x; l < per_owner; l += PRB_THREADS)
+                        if (l * P.world + o < n) prb_smem[l * P.world + o] = P.contrib_in[(int64_t)o * P.vp + l0 + l];
+            }
             if (threadIdx.x < 4) prb_smem[PRB_H + threadIdx.x] = 0.f; // what a padding slot gathers
             __syncthreads();
             // every warp streams one contiguous piece of this CTA's steps of the bin
@@ -561,7 +585,9 @@ void vglb_pr_bins_params(const vglb_graph *g, const float *contrib_in, PrbBinPar
     P->slot = B->d_slot;
     P->nb = B->nb;
     P->cold_chunk0 = B->cold_chunk0;
-    P->cols = g->V;
+    P->cols = g->comm ? g->cols : (int64_t)g->V;
+    P->world = g->comm ? g->part_world : 1;
+    P->vp = g->vp;
     P->nruns = B->nruns;
     P->cta_ns = NULL;
 }

@@ -131,7 +131,7 @@ class SingleGpuRunner:
         self.iters_per_step = pr_iters if workload == "pr" else 1
         self.edges_per_step = self.g.E * self.iters_per_step
         self.out = ctx.empty(V, np.float32 if self.dtype == "f32" else np.int32)
-        self.dominant_kernel = {"pr": "pr_sweep_kernel", "bfs": "bfs_td_kernel + bfs_bu_kernel (whole run)",
+        self.dominant_kernel = {"pr": "pr_bin_kernel + pr_cold_bin_kernel + pr_sweep_kernel + pr_finish_kernel (one sweep)", "bfs": "bfs_td_kernel + bfs_bu_kernel (whole run)",
                                 "sssp": "sssp_relax_flat_kernel + sssp_select_kernel (whole run)", "cc": "cc_hook_kernel + cc_jump_kernel (whole run)"}[workload]
         self.weights = self.g.synthetic_weights(vgl.MASTER_SEED ^ 0x5555) if workload == "sssp" else None
         self.sources = None
