@@ -243,10 +243,14 @@ static int sssp_partitioned_dense(vglb_ctx *ctx, vglb_graph *g, const float *d_w
 // finds the row of its edge with a 5-step shuffle search over the prefix, so all lanes carry an edge whatever the degree
 // mix, loads of one row are consecutive (the queue is ascending, so neighbouring rows are neighbours in memory too),
 // and SSSP_FLAT_UNROLL independent index/weight loads are in flight per lane before the dependent distance gathers.
+#ifndef SSSP_FLAT_UNROLL
 #define SSSP_FLAT_UNROLL 4
+#endif
 #define SSSP_BIG_CHUNK 8192
 #define SSSP_BIG_DEGREE 512  // rows with at least this many edges are relaxed by CTAs (the graph-wide tier border is 4096)
+#ifndef SSSP_WARP_EDGES
 #define SSSP_WARP_EDGES 1280
+#endif
 
 // relax one edge: atomicMin on the uint32 view after a plain read that filters the losers; the winner marks the vertex
 // as due in the near (new distance below the threshold) or the far bitmap
