@@ -403,8 +403,8 @@ __global__ void __launch_bounds__(PR_THREADS, PR_MIN_CTAS) pr_cold_bin_kernel(co
     __shared__ float s_stage[PR_WARPS][2 * PRB_STAGE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int end_step = P.bin_nkchunks * PRB_SPC;
-    const int u = (P.bins.cold_chunk0 * PRB_SPC) / PR_COLD_SPU + blockIdx.x * PR_WARPS + warp; // units of PR_COLD_SPU steps
-    if (u * PR_COLD_SPU < end_step) prb_unit<true>(P.bins, pol, NULL, u * PR_COLD_SPU, (u + 1) * PR_COLD_SPU, end_step, lane, s_stage[warp]);
+    const int s0 = P.bins.cold_chunk0 * PRB_SPC + (blockIdx.x * PR_WARPS + warp) * PR_COLD_SPU; // units of PR_COLD_SPU steps
+    if (s0 < end_step) prb_unit<true>(P.bins, pol, NULL, s0, min(s0 + PR_COLD_SPU, end_step), end_step, lane, s_stage[warp]);
 }
 
 __global__ void __launch_bounds__(PR_THREADS) pr_finish_kernel(const __grid_constant__ PrParams P)
@@ -782,7 +782,7 @@ int64_t vglb_pr_plan(const vglb_graph *g, int32_t rows, PrParams *P)
         P->bin_finish_blocks = P->bin_long_blocks + (int32_t)ceil_div64(B->rows - B->long_rows, PR_THREADS);
         P->bin_nkchunks = B->nkchunks;
         vglb_pr_bins_params(g, NULL, &P->bins);
-        P->bin_cold_blocks = (int32_t)ceil_div64((int64_t)(B->nkchunks - B->cold_chunk0) * PRB_SPC / PR_COLD_SPU, PR_WARPS);
+        P->bin_cold_blocks = (int32_t)ceil_div64(ceil_div64((int64_t)(B->nkchunks - B->cold_chunk0) * PRB_SPC, PR_COLD_SPU), PR_WARPS);
         P->ntasks = 0;
         P->heavy_blocks = 0;
     }

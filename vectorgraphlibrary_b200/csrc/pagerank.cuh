@@ -27,7 +27,7 @@
 #define PR_VE_SEGS_PER_WARP 8     // 32-row segments of the padded tail copy handled by one warp (r2 A/B with the column bins: 16 -> 0.611, 8 -> 0.527 ms)
 #endif
 #ifndef PR_COLD_SPU
-#define PR_COLD_SPU 8            // steps of the cold bin handled by one warp of pr_cold_bin_kernel (1: 212 us, 8: 137 us at RMAT-24)
+#define PR_COLD_SPU 8            // steps of the cold bin handled by one warp of pr_cold_bin_kernel (A/B at RMAT-24, ms per sweep: 1 -> 0.618, 2 -> 0.578, 4 -> 0.548, 8 -> 0.531, 16 -> 0.543, 32 -> 0.576)
 #endif
 #ifndef PR_ZERO_ROWS_PER_CTA
 #define PR_ZERO_ROWS_PER_CTA 4096 // rows without out-edges handled by one CTA
@@ -146,6 +146,9 @@ struct L2Pol
 #define PRB_SPC (PRB_CHUNK / PRB_STEP)  // steps per chunk
 #define PRB_ALIGN 4                     // runs start at multiples of this many slots
 #define PRB_STAGE 128                   // a step closes at most PRB_STEP / PRB_ALIGN runs
+#ifndef PRB_L2_AHEAD
+#define PRB_L2_AHEAD 0                   // steps ahead whose columns and metadata are pulled into L2 by a bulk prefetch (0 = off; A/B at RMAT-24: 0 -> 0.529, 3 -> 0.545, 6 -> 0.548, 12 -> 0.574 ms per sweep)
+#endif
 
 __device__ __forceinline__ uint4 prb_ld_v4u(const uint4 *p, uint64_t pol)
 {
@@ -207,6 +210,12 @@ __device__ __forceinline__ PrbStep prb_load_step(const PrbBinParams &P, const L2
     return d;
 }
 
+// pull `bytes` (a multiple of 16, 16-byte aligned) into L2 ahead of the loads that will want them
+__device__ __forceinline__ void prb_prefetch_l2(const void *p, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // One unit = the steps [s0, s1) of one bin: emits the sums of the runs that START in it. The warp ignores the leading part of a
 // run that started earlier and runs on past s1 until the next start (in those steps only the lanes up to the first start
 // gather). Latency: the unit is a stream — columns and metadata are fetched two steps ahead, and the sums a step closes are
@@ -231,6 +240,14 @@ __device__ __forceinline__ void prb_unit(const PrbBinParams &P, const L2Pol &pol
         const bool ahead2 = s + 2 <= s1 || (beyond && total == 0);
         PrbStep nx2 = nxt;
         if (ahead2 && s + 2 < bin_end_step) nx2 = prb_load_step(P, pol, s + 2, lane, COLD);
+        if (PRB_L2_AHEAD > 0 && s + PRB_L2_AHEAD < min(s1 + 1, bin_end_step))
+        {
+            // (the register prefetch above then meets L2 instead of DRAM latency)
+            const int64_t sp = s + PRB_L2_AHEAD;
+            if (!COLD && lane == 0) prb_prefetch_l2(P.wcol + sp * PRB_STEP, PRB_STEP * 2);
+            if (COLD && lane == 0) prb_prefetch_l2(P.cold + (sp - (int64_t)P.cold_chunk0 * PRB_SPC) * PRB_STEP, PRB_STEP * 4);
+            if (lane == 1) prb_prefetch_l2(P.meta + sp * 32, 128);
+        }
         const int ra = run0 + lane - 1, rb = ra + 32;
         const int sa = (lane < total && ra >= r_first && ra < r_end) ? __ldg(P.run_slot + ra) : -1;
         const int sb = (lane + 32 < total && rb >= r_first && rb < r_end) ? __ldg(P.run_slot + rb) : -1;
