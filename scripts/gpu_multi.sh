@@ -16,7 +16,7 @@ for w in $WL; do
 import json,sys
 try:
     d=json.loads(open('gpurun_out/bench_${w}_n$N.json').read().strip().splitlines()[-1])
-    print('$w', 'N=$N', 'GTEPS', round(d['value'],2), 'ms/step', round(d['ms_per_step'],3), 'e2e', round(d['e2e']['value'],2), 'frac', round(d['roofline']['frac'],3), d['config']['partition'][-90:])
+    print('$w', 'N=$N', 'GTEPS', round(d['value'],2), 'ms/step', round(d['ms_per_step'],3), 'e2e', round(d['e2e']['value'],2), 'frac', round(d['roofline']['frac'],3), d.get('partition','')[-90:])
 except Exception as e: print('no json', e)
 "
 done

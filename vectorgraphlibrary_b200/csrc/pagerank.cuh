@@ -50,7 +50,8 @@ struct vglb_graph;
 // ---- column-binned heavy rows (pagerank_bins.cu) --------------------------------------------------------------------------
 #define PRB_H 49152     // columns per bin: its slice of the contribution vector fills 192 KB of shared memory
 #define PRB_RC 4096     // a row's edges are cut into chunks of this many before binning: no (bin,row) run is longer
-#define PRB_MAX_BINS 32 // shared-memory bins; columns at or above PRB_MAX_BINS * PRB_H form the cold bin
+#define PRB_MIN_BINS 32  // shared-memory bins used (columns beyond them form the cold bin)
+#define PRB_MAX_BINS 128 // what the VGLB_PR_BINS developer knob may ask for
 
 struct PrBins
 {
