@@ -11,6 +11,7 @@ with vgl.Context(0) as ctx:
     H["ptr"][:], H["adj"][:], H["fwd"][:] = ptr, adj, g0.orig_to_sorted()
     g0.free()
     L = vgl.lib()
+    vgl._check(L.vglb_set_upload_hint(ctx.h, vgl.HINT_PAGERANK))
     for it in range(4):
         ctx.synchronize(); t0 = time.perf_counter()
         g = vgl.Graph.from_csr(ctx, H["ptr"], H["adj"], H["fwd"]); ctx.synchronize(); t1 = time.perf_counter()

@@ -625,7 +625,8 @@ extern "C" int vglb_graph_from_csr(vglb_ctx *ctx, int32_t V, int64_t E, const in
             if (!bad)
             {
                 g->pr_bins_tried = 1;
-                BUILD_TRY(vglb_pr_bins_build_rows(ctx, g, heavy_rows));
+                const int rcb = vglb_pr_bins_build_rows(ctx, g, heavy_rows);
+                if (rcb != VGLB_OK && rcb != VGLB_ENOMEM) BUILD_TRY(rcb); // (no memory for the binned copy: PageRank falls back to warp tasks)
             }
         }
     }

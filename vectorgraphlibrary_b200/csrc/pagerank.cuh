@@ -65,6 +65,7 @@ struct PrBins
     int64_t slots;
     int32_t nruns;
     int grid;            // persistent CTAs (one per SM)
+    int traced;          // VGLB_PR_BIN_TRACE printed this graph's per-CTA times
     uint16_t *d_wcol;    // column - bin * PRB_H of every slot of the shared-memory bins (PRB_H = padding)
     int32_t *d_cold;     // column of every slot of the cold bin (-1 = padding)
     uint32_t *d_meta;    // per lane and step: static part of the segmented sum

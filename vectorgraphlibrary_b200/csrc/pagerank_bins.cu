@@ -609,9 +609,8 @@ int vglb_pr_bins_launch(vglb_ctx *ctx, vglb_graph *g, const float *contrib_in)
     }
     PrbBinParams P;
     vglb_pr_bins_params(g, contrib_in, &P);
-    static int traced = 0;
     long long *d_ns = NULL;
-    if (!traced && getenv("VGLB_PR_BIN_TRACE") && g->V > (1 << 20))
+    if (!B->traced && getenv("VGLB_PR_BIN_TRACE") && g->V > (1 << 20))
     {
         CUDA_TRY(vglb_dev_alloc(&d_ns, (size_t)B->grid * 8));
         P.cta_ns = d_ns;
@@ -621,7 +620,7 @@ int vglb_pr_bins_launch(vglb_ctx *ctx, vglb_graph *g, const float *contrib_in)
     ctx->launches++;
     if (d_ns)
     {
-        traced = 1;
+        B->traced = 1;
         std::vector<long long> ns((size_t)B->grid);
         std::vector<int32_t> c0((size_t)B->grid + 1), b0((size_t)B->nb + 2);
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
