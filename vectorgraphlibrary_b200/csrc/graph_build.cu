@@ -120,6 +120,29 @@ __global__ void indegree_noloops_rows_kernel(const int64_t *__restrict__ ptr, co
     }
 }
 
+// The same for a chunk of rows with fewer than 32 edges each (the tail of the degree-sorted CSR, half of it without edges):
+// one lane per row — with a warp per row the chunk is a chain of dependent loads per row, 1.6 ms for the 15.7 M tail rows of
+// the BASELINE PageRank graph, all of it after the upload has finished.
+__global__ void indegree_noloops_short_rows_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ adj, int32_t row0, int32_t row1,
+                                                   int64_t e_lo, int64_t e_hi, int32_t V, int32_t *__restrict__ indeg, int *__restrict__ bad)
+{
+    for (int64_t v = row0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < row1; v += (int64_t)gridDim.x * blockDim.x)
+    {
+        const int64_t s = ptr[v], e = ptr[v + 1];
+        if (s < e_lo || e > e_hi || s > e)
+        {
+            *bad = 1;
+            continue;
+        }
+        for (int64_t p = s; p < e; p++)
+        {
+            const int32_t d = adj[p];
+            if ((uint32_t)d >= (uint32_t)V) *bad = 1;
+            else if (d != (int32_t)v) atomicAdd(&indeg[d], 1);
+        }
+    }
+}
+
 // row pointers of a caller-supplied CSR: ptr[0] == 0, non-decreasing, ptr[rows] == E
 __global__ void csr_ptr_check_kernel(const int64_t *__restrict__ ptr, int32_t rows, int64_t E, int *__restrict__ bad)
 {
@@ -514,10 +537,20 @@ extern "C" int vglb_graph_from_csr(vglb_ctx *ctx, int32_t V, int64_t E, const in
         cleanup();
         return VGLB_EINVAL;
     }
+    const bool csr_trace = getenv("VGLB_CSR_TRACE") != NULL; // developer aid: host timeline of the upload on stderr
+    struct timespec ts0;
+    clock_gettime(CLOCK_MONOTONIC, &ts0);
+    auto stamp = [&](const char *what) {
+        if (!csr_trace) return;
+        struct timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        fprintf(stderr, "from_csr: %-44s %8.2f ms\n", what, 1e3 * (double)(ts.tv_sec - ts0.tv_sec) + 1e-6 * (double)(ts.tv_nsec - ts0.tv_nsec));
+    };
     int *d_bad = (int *)(ctx->d_counters + 56);
     BUILD_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
     const size_t eb = (size_t)(E ? E : 1) * 4;
     BUILD_CUDA(vglb_dev_alloc(&g->d_out_ptr, ((size_t)V + 2) * 8));
+    stamp("first allocation");
     BUILD_CUDA(vglb_dev_alloc(&g->d_out_adj, eb + 16));
     // The upload is PCIe-bound (1.3 GB at ~55 GB/s for the BASELINE PageRank graph), so the device works while it runs: the
     // adjacency goes up in 8 row-aligned chunks on a second stream and the in-degrees without self loops — what PageRank's
@@ -562,6 +595,7 @@ extern "C" int vglb_graph_from_csr(vglb_ctx *ctx, int32_t V, int64_t E, const in
     // the upload. The border nearest to the end of those rows is moved there.
     int heavy_chunk = -1; // chunk that ends the heavy rows
     int32_t heavy_rows = 0;
+    const int32_t short_rows_from = chunks > 1 ? rows_with_degree_at_least(32) : V; // (a small graph goes up as one chunk)
     if (chunks > 1 && (ctx->upload_hint & VGLB_HINT_PAGERANK) && vglb_pr_bins_wanted(g))
     {
         cudaPointerAttributes attr;
@@ -591,6 +625,24 @@ extern "C" int vglb_graph_from_csr(vglb_ctx *ctx, int32_t V, int64_t E, const in
             return VGLB_EINVAL;
         }
     }
+    // the other arrays of the caller: queued on the copy stream behind the adjacency (before the host waits for anything)
+    BUILD_CUDA(vglb_dev_alloc(&g->d_fwd, (size_t)V * 4));
+    BUILD_CUDA(vglb_dev_alloc(&g->d_bwd, (size_t)V * 4));
+    if (h_in_ptr)
+    {
+        BUILD_CUDA(vglb_dev_alloc(&g->d_in_ptr, ((size_t)V + 2) * 8));
+        BUILD_CUDA(vglb_dev_alloc(&g->d_in_adj, eb + 16));
+    }
+    bool others_queued = false;
+    auto queue_others = [&]() -> cudaError_t {
+        if (others_queued) return cudaSuccess;
+        others_queued = true;
+        cudaError_t e = cudaSuccess;
+        if (h_orig_to_sorted) e = cudaMemcpyAsync(g->d_fwd, h_orig_to_sorted, (size_t)V * 4, cudaMemcpyHostToDevice, ctx->copy_stream);
+        if (e == cudaSuccess && h_in_ptr) e = cudaMemcpyAsync(g->d_in_ptr, h_in_ptr, ((size_t)V + 1) * 8, cudaMemcpyHostToDevice, ctx->copy_stream);
+        if (e == cudaSuccess && h_in_ptr) e = cudaMemcpyAsync(g->d_in_adj, h_in_adj, (size_t)E * 4, cudaMemcpyHostToDevice, ctx->copy_stream);
+        return e;
+    };
     if (heavy_chunk >= 0) // pinned source: queue every copy first
         for (int k = 0; k < chunks; k++)
         {
@@ -599,6 +651,7 @@ extern "C" int vglb_graph_from_csr(vglb_ctx *ctx, int32_t V, int64_t E, const in
                 BUILD_CUDA(cudaMemcpyAsync(g->d_out_adj + e0, h_out_adj + e0, (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
             BUILD_CUDA(cudaEventRecord(ctx->ev_chunk[k], ctx->copy_stream));
         }
+    if (heavy_chunk >= 0) BUILD_CUDA(queue_others());
     for (int k = 0; k < chunks; k++)
     {
         const int32_t row0 = border[k], row1 = border[k + 1];
@@ -611,8 +664,13 @@ extern "C" int vglb_graph_from_csr(vglb_ctx *ctx, int32_t V, int64_t E, const in
                 BUILD_CUDA(cudaEventRecord(ctx->ev_chunk[k], ctx->copy_stream));
             }
             BUILD_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[k], 0));
-            indegree_noloops_rows_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(g->d_out_ptr, g->d_out_adj, row0, row1, e0, e1, V,
-                                                                                     g->d_indeg_noloops, d_bad);
+            // (rows are degree-sorted: a chunk that starts at or after the first row with fewer than 32 edges has only such rows)
+            if (row0 >= short_rows_from)
+                indegree_noloops_short_rows_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(g->d_out_ptr, g->d_out_adj, row0, row1, e0, e1, V,
+                                                                                               g->d_indeg_noloops, d_bad);
+            else
+                indegree_noloops_rows_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(g->d_out_ptr, g->d_out_adj, row0, row1, e0, e1, V,
+                                                                                         g->d_indeg_noloops, d_bad);
             BUILD_CUDA(cudaGetLastError());
             ctx->launches++;
         }
@@ -620,28 +678,21 @@ extern "C" int vglb_graph_from_csr(vglb_ctx *ctx, int32_t V, int64_t E, const in
         {
             // (the row pointers were checked by csr_ptr_check_kernel: a bad array fails the call below, not the build)
             int bad = 0;
+            stamp("copies queued");
             BUILD_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             BUILD_CUDA(cudaStreamSynchronize(ctx->stream));
+            stamp("heavy rows have landed");
             if (!bad)
             {
                 g->pr_bins_tried = 1;
                 const int rcb = vglb_pr_bins_build_rows(ctx, g, heavy_rows);
                 if (rcb != VGLB_OK && rcb != VGLB_ENOMEM) BUILD_TRY(rcb); // (no memory for the binned copy: PageRank falls back to warp tasks)
+                stamp("column bins built");
             }
         }
     }
-    if (h_in_ptr)
-    {
-        BUILD_CUDA(vglb_dev_alloc(&g->d_in_ptr, ((size_t)V + 2) * 8));
-        BUILD_CUDA(vglb_dev_alloc(&g->d_in_adj, eb + 16));
-        BUILD_CUDA(cudaMemcpyAsync(g->d_in_ptr, h_in_ptr, ((size_t)V + 1) * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
-        BUILD_CUDA(cudaMemcpyAsync(g->d_in_adj, h_in_adj, (size_t)E * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
-    }
-    BUILD_CUDA(vglb_dev_alloc(&g->d_fwd, (size_t)V * 4));
-    BUILD_CUDA(vglb_dev_alloc(&g->d_bwd, (size_t)V * 4));
+    BUILD_CUDA(queue_others());
     const unsigned vgrid = (unsigned)ceil_div64(V, 256);
-    if (h_orig_to_sorted)
-        BUILD_CUDA(cudaMemcpyAsync(g->d_fwd, h_orig_to_sorted, (size_t)V * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
     if (chunks > 1 && !vglb_pr_bins_wanted(g))
     {
         // the host is idle while the DMA runs: PageRank's warp-task table of the rows with >= 32 edges (pagerank.cu) is built
@@ -670,8 +721,10 @@ extern "C" int vglb_graph_from_csr(vglb_ctx *ctx, int32_t V, int64_t E, const in
         }
     }
     int bad = 0;
+    stamp("checks queued");
     BUILD_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     BUILD_CUDA(cudaStreamSynchronize(ctx->stream));
+    stamp("uploads and checks done");
     if (bad)
     {
         vglb_set_error("vglb_graph_from_csr: not a CSR (row pointers must be non-decreasing from 0 to E, vertex ids in [0, V), "
@@ -680,6 +733,7 @@ extern "C" int vglb_graph_from_csr(vglb_ctx *ctx, int32_t V, int64_t E, const in
         return VGLB_EINVAL;
     }
     BUILD_TRY(vglb_graph_compute_tiers(ctx, g));
+    stamp("tiers");
     vglb_graph_set_unpartitioned(g);
     *out_graph = g;
     return VGLB_OK;

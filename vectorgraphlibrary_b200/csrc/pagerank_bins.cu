@@ -216,7 +216,8 @@ __global__ void prb_run_pos_kernel(const int64_t *__restrict__ pos_scan, const i
 
 // Shared-memory bank conflicts: a warp's e-th gather reads slot e of every lane. Inside a run the order of the slots is free, so
 // every lane sorts the slots of each run piece it holds by (column - lane) mod 32: its e-th slot then sits near bank lane + 2 e,
-// a different bank for every lane (measured wavefronts per gather instruction: 4.4 -> see profiles/r2_pr_bins_ncu.txt).
+// a different bank for every lane. Measured: wavefronts per gather instruction 4.4 -> 2.9, time per sweep unchanged (the kernel
+// is not bound by the shared-memory pipe), so the pass is off unless VGLB_PR_BANK_SORT is set.
 __global__ void prb_sort_lanes_kernel(uint4 *__restrict__ wcol8, const uint32_t *__restrict__ meta, int64_t nsteps)
 {
     const int lane = threadIdx.x & 31;
@@ -486,7 +487,7 @@ int vglb_pr_bins_build_rows(vglb_ctx *ctx, vglb_graph *g, int32_t rows)
     prb_runs_kernel<<<(unsigned)ceil_div64(n + nc, 256), 256, 0, st>>>(d_cnt, d_run_pos, d_pos_scan, d_flag_scan, d_bin_start, nch, nc,
                                                                       B->d_meta, B->d_run_slot);
     PRB_CUDA(cudaGetLastError());
-    if (w_smem > 0 && !getenv("VGLB_PR_NO_BANK_SORT")) // (developer A/B knob)
+    if (w_smem > 0 && getenv("VGLB_PR_BANK_SORT")) // (developer A/B knob; off: 0.35 ms of the build and no faster sweeps)
     {
         const int64_t steps_smem = w_smem / PRB_STEP;
         prb_sort_lanes_kernel<<<(unsigned)ceil_div64(steps_smem * 32, 256), 256, 0, st>>>(reinterpret_cast<uint4 *>(B->d_wcol), B->d_meta, steps_smem);
