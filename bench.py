@@ -11,8 +11,9 @@ convention: iterations x graph edges / time / 1e9 (performance_stats.hpp:272-275
   value        device-timed (CUDA events on the library's stream), graph resident in HBM, max over ranks
   e2e          the same metric through the C ABI with HOST buffers: every step copies the VectCSR arrays the reference
                host build owns (row pointers, adjacency, id map; pinned memory) to HBM (vglb_graph_from_csr =
-               VGL_Graph::move_to_device), runs the algorithm and copies the result back
-  roofline     dominant kernel: algorithmic bytes per launch (SURVEY §8d formulas evaluated with the library's counters) /
+               VGL_Graph::move_to_device; the host announces PageRank with vglb_set_upload_hint), runs the algorithm, reorders the
+               result to the caller's ORIGINAL numbering on the device (N = 1) and copies it back
+  roofline     dominant kernel(s) (PageRank: the four kernels of one sweep): algorithmic bytes per launch (SURVEY §8d formulas evaluated with the library's counters) /
                average launch duration, against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline the reference's own multicore (OpenMP) implementation (oracle/_ref: unmodified VGL, timing build) on this
                box's host cores, on the SAME graph when it fits the time budget (configs 1 and 2 do), else a bounded sample

@@ -211,9 +211,12 @@ class SingleGpuRunner:
                 w.free()
             else:
                 g.cc(out)
-            vgl._check(L.vglb_memcpy_d2h(ctx.h, H["out"].ctypes.data, out.ptr, d2h))
+            # the caller gets the result in ITS numbering: VerticesArray::reorder(ORIGINAL) on the device, then the download
+            res = g.reorder(out, vgl.SCATTER, vgl.ORIGINAL)
+            vgl._check(L.vglb_memcpy_d2h(ctx.h, H["out"].ctypes.data, res.ptr, d2h))
             ctx.synchronize()
             dt = time.perf_counter() - t0
+            res.free()
             out.free()
             g.free()
             if i > 0:  # first pass warms the allocator
