@@ -22,8 +22,8 @@ convention: iterations x graph edges / time / 1e9 (performance_stats.hpp:272-275
   extras.workloads   after the headline, outside its timed region: the other BASELINE configs with the same measurements —
                bfs (config 4: DO-BFS Kronecker s26 ef16), sssp (config 3: uniform s24 ef32), cc (RMAT s24 ef16 symmetrised),
                bfs20 (config 1: BFS RMAT s20 ef16, N = 1, with the CPU reference on the same graph and sources);
-               at N > 1 also bfs_strong (config 4 strong scaling: the same s26 graph at every N) and at N = 8 config5
-               (CC + PageRank on RMAT scale-28 ef16)
+               at N > 1 also bfs_strong (config 4 strong scaling: the same s26 graph at every N); config 5 (CC + PageRank on
+               RMAT scale-28 ef16, 8 GPUs) is `--workload config5`
 
 `--impl reference` times the reference's CPU path alone (same metric / config / unit). Under torchrun (N > 1) every rank
 owns a 1D vertex range of the graph; `--scaling strong` keeps the graph fixed as N grows.
@@ -502,8 +502,8 @@ def ours(args):
                 plan.append(("bfs20_top_down", "bfs20", 20, True, 16, True))
             else:
                 plan.append(("bfs_strong", "bfs", WORKLOADS["bfs"][1], False, 16, False))
-            if world == 8:
-                plan += [("config5_pr_s28", "pr", 28, False, 5, False), ("config5_cc_s28", "cc", 28, False, 3, False)]
+            # (config 5 — CC + PageRank on RMAT scale-28, 8 GPUs — is `--workload config5`: 4.3 G edges take minutes to
+            # generate and partition, too long for the default line)
         for key, wl, sc, wk, steps, td_only in plan:
             # every rank takes the same decision (the clock of rank 0 is broadcast through the max)
             over = B.max_float(1.0 if time.perf_counter() > deadline else 0.0) > 0.0
