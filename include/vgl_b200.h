@@ -204,7 +204,9 @@ int vglb_pagerank_ex(vglb_ctx *ctx, vglb_graph *g, int iters, float damping, con
                      vglb_stats *stats);
 
 /* BFS levels (algorithms/bfs/bfs.hpp:5-86; DO heuristic change_state.hpp:100-141): source = 1, unreachable = -1,
- * SCATTER numbering. direction_optimising needs a graph built WITH_INCOMING. alpha/beta <= 0 select 15 / 18. */
+ * SCATTER numbering. direction_optimising uses the incoming CSR: a one-GPU graph without one (vglb_graph_from_csr with NULL incoming
+ * arrays, vglb_graph_from_edges without WITH_INCOMING) gets it derived on the device by the first such call; a partitioned graph
+ * must be built WITH_INCOMING. alpha/beta <= 0 select 15 / 18. */
 typedef struct vglb_bfs_opts
 {
     int32_t direction_optimising;

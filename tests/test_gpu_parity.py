@@ -520,3 +520,26 @@ def test_baseline_size_properties(vgl, ctx, oracle):
     nxt = (1.0 - 0.85) / V + 0.85 * (sums + dangling)
     assert oracle.rel_l1(r21.to_numpy(), nxt) <= PR_TOL, "one fp64 sweep on top of the 20-sweep result gives the 21-sweep result"
     G.free()
+
+
+def test_direction_optimising_bfs_derives_the_incoming_csr(vgl, ctx, oracle):
+    """A graph uploaded without incoming arrays: the first direction-optimising vglb_bfs derives them on the device; the levels
+    are those of the graph built with VGLB_GRAPH_WITH_INCOMING (and of the oracle)."""
+    O = oracle
+    scale, ef = 15, 16
+    V = 1 << scale
+    src, dst = O.generate_edges(O.GEN_RMAT if hasattr(O, "GEN_RMAT") else 0, scale, ef, 0xD0B)
+    G0 = vgl.Graph.from_edges(ctx, V, src, dst, vgl.GRAPH_WITH_INCOMING)
+    ptr, adj = G0.layout()
+    fwd = G0.orig_to_sorted()
+    outdeg = np.bincount(src, minlength=V)
+    s = int(O.pick_sources(V, outdeg, 1, 0xD0B)[0])
+    want, _ = G0.bfs(int(fwd[s]), direction_optimising=True)
+    want = G0.to_original(want)
+    G0.free()
+    G = vgl.Graph.from_csr(ctx, ptr, adj, fwd)  # outgoing direction only
+    got, st = G.bfs(int(fwd[s]), direction_optimising=True)
+    got = G.to_original(got)
+    G.free()
+    assert np.array_equal(got, want)
+    assert np.array_equal(got, O.OracleGraph(V, src, dst).bfs(s)[0])

@@ -1144,8 +1144,11 @@ extern "C" int vglb_bfs(vglb_ctx *ctx, vglb_graph *g, int32_t source, int32_t *d
     const bool dopt = opts && opts->direction_optimising;
     if (dopt && !g->d_in_ptr)
     {
-        vglb_set_error("vglb_bfs: direction-optimising BFS needs a graph built with VGLB_GRAPH_WITH_INCOMING");
-        return VGLB_EINVAL;
+        // The bottom-up levels need the incoming CSR. A graph uploaded without it (vglb_graph_from_csr with NULL incoming arrays)
+        // gets it here, once, from the outgoing one: a device sort of the edges is cheaper than a second 4.8 GB PCIe upload
+        // (Kronecker s26: see DESIGN.md §6).
+        int rc_in = vglb_graph_derive_incoming(ctx, g);
+        if (rc_in != VGLB_OK) return rc_in;
     }
     long long alpha = (opts && opts->alpha > 0) ? opts->alpha : BFS_DEFAULT_ALPHA;
     long long beta = (opts && opts->beta > 0) ? opts->beta : BFS_DEFAULT_BETA;

@@ -172,7 +172,10 @@ class SingleGpuRunner:
             h_out, _ = pinned_array(vgl, g.V, np.float32 if self.dtype == "f32" else np.int32)
             host = {"ptr": h_ptr, "adj": h_adj, "fwd": h_fwd, "out": h_out, "in_ptr": None, "in_adj": None, "w": None}
             del ptr, adj
-            if self.workload == "bfs":
+            # BFS: the bottom-up levels need the incoming CSR. By default only the outgoing direction goes up and vglb_bfs derives
+            # the incoming one on the device (a sort of the edges beats a second PCIe upload of the same size);
+            # VGLB_E2E_UPLOAD_INCOMING=1 uploads the caller's incoming arrays instead (A/B).
+            if self.workload == "bfs" and self.bfs_direction_optimising and os.environ.get("VGLB_E2E_UPLOAD_INCOMING"):
                 iptr, iadj = g.layout(incoming=True)
                 host["in_ptr"], _ = pinned_array(vgl, g.V + 1, np.int64)
                 host["in_adj"], _ = pinned_array(vgl, g.E, np.int32)
