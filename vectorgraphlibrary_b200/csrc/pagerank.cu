@@ -259,18 +259,30 @@ __device__ __forceinline__ void pr_tail_segments(const PrParams &P, const L2Pol 
         const int32_t *pa = P.ve_adj + b0 + lane, *pb = P.ve_adj + b1 + lane;
         float acc_a = 0.f, acc_b = 0.f;
         const int dmax = max(d0, d1);
-        for (int j = 0; j < dmax; j += 2)
+        // PR_TAIL_J neighbours of each of the two rows per trip: their index loads go out together, then their gathers (a trip
+        // is two dependent round trips whatever PR_TAIL_J is)
+        for (int j = 0; j < dmax; j += PR_TAIL_J)
         {
-            const int32_t a0 = j < d0 ? ld_stream_s32(pa + j * 32, pol.stream) : self_a;
-            const int32_t a1 = j + 1 < d0 ? ld_stream_s32(pa + (j + 1) * 32, pol.stream) : self_a;
-            const int32_t c0 = j < d1 ? ld_stream_s32(pb + j * 32, pol.stream) : self_b;
-            const int32_t c1 = j + 1 < d1 ? ld_stream_s32(pb + (j + 1) * 32, pol.stream) : self_b;
-            const float x0 = a0 != self_a ? pr_gather(P, pol, a0) : 0.f;
-            const float x1 = a1 != self_a ? pr_gather(P, pol, a1) : 0.f;
-            const float y0 = c0 != self_b ? pr_gather(P, pol, c0) : 0.f;
-            const float y1 = c1 != self_b ? pr_gather(P, pol, c1) : 0.f;
-            acc_a += x0 + x1;
-            acc_b += y0 + y1;
+            int32_t a[PR_TAIL_J], c[PR_TAIL_J];
+#pragma unroll
+            for (int u = 0; u < PR_TAIL_J; u++)
+            {
+                a[u] = j + u < d0 ? ld_stream_s32(pa + (j + u) * 32, pol.stream) : self_a;
+                c[u] = j + u < d1 ? ld_stream_s32(pb + (j + u) * 32, pol.stream) : self_b;
+            }
+            float x[PR_TAIL_J], y[PR_TAIL_J];
+#pragma unroll
+            for (int u = 0; u < PR_TAIL_J; u++)
+            {
+                x[u] = a[u] != self_a ? pr_gather(P, pol, a[u]) : 0.f;
+                y[u] = c[u] != self_b ? pr_gather(P, pol, c[u]) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < PR_TAIL_J; u += 2)
+            {
+                acc_a += x[u] + x[u + 1];
+                acc_b += y[u] + y[u + 1];
+            }
         }
         if (row_a < P.zero_first) pr_epilogue(P, pol, row_a, acc_a, dang, dang_local);
         if (two && row_b < P.zero_first) pr_epilogue(P, pol, row_b, acc_b, dang, dang_local);

@@ -26,6 +26,9 @@
 #ifndef PR_VE_SEGS_PER_WARP
 #define PR_VE_SEGS_PER_WARP 8     // 32-row segments of the padded tail copy handled by one warp (r2 A/B with the column bins: 16 -> 0.611, 8 -> 0.527 ms)
 #endif
+#ifndef PR_TAIL_J
+#define PR_TAIL_J 2               // neighbours of a tail row fetched per trip of its loop (even)
+#endif
 #ifndef PR_COLD_SPU
 #define PR_COLD_SPU 8            // steps of the cold bin handled by one warp of pr_cold_bin_kernel (A/B at RMAT-24, ms per sweep: 1 -> 0.618, 2 -> 0.578, 4 -> 0.548, 8 -> 0.531, 16 -> 0.543, 32 -> 0.576)
 #endif
