@@ -410,6 +410,9 @@ class Bench:
             "dtype": runner.dtype, "config": cfg, "partition": runner.partition,
             "roofline": {"bound": "hbm", "kernel": runner.dominant_kernel, "achieved": achieved, "peak": self.peak, "unit": "GB/s",
                          "frac": achieved / self.peak, "traffic": ncu_traffic(workload, self.world) if scale == WORKLOADS[workload][1] else None,
+                         "traffic_source": "profiles/r2_pr_sweep_ncu_full.txt: dram__bytes_read + dram__bytes_write of the four kernels of one sweep, "
+                                           "one `ncu --set full` capture of this command (committed; not re-measured in this run)"
+                         if workload == "pr" and self.world == 1 and scale == WORKLOADS[workload][1] else None,
                          "peak_source": self.peak_src, "bytes_per_launch": kern_bytes, "ms_per_launch": kern_s * 1e3},
             "e2e": {"value": edges_per_step / e2e["seconds"] / 1e9, "unit": METRIC, "h2d_bytes_per_step": e2e["h2d"],
                     "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e["seconds"] * 1e3},
