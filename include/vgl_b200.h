@@ -185,7 +185,10 @@ typedef struct vglb_stats
 /* ---- fused algorithms (the four call sites of SURVEY §8 a11-a14) ---- */
 
 /* PageRank, multicore semantics (algorithms/pr/pr.hpp:7-148): r'[u] = k + d*(sum_{u->v, v!=u} r[v]/indeg_noloops(v) + D).
- * Runs exactly `iters` sweeps; d_ranks (fp32[V]) is returned in SCATTER numbering. */
+ * Runs exactly `iters` sweeps; d_ranks (fp32[V]) is returned in SCATTER numbering. The first call on a graph builds what the
+ * sweep needs beyond the CSR (inverse in-degrees, padded copy of the short rows, column-binned copy of the rows with >= 32 edges:
+ * +0.9 GB at scale 24; or earlier, behind the upload: vglb_set_upload_hint). Sums are taken in a fixed order: two runs give the
+ * same bits. */
 int vglb_pagerank(vglb_ctx *ctx, vglb_graph *g, int iters, float damping, float *d_ranks, vglb_stats *stats);
 /* How the dangling mass D is summed. The reference's reduce (pr.hpp:94-103 -> multicore/reduce.hpp:18-31) is an OpenMP static-
  * chunk fp32 reduction whose rounding error depends on the thread count and exceeds the 1e-6 parity tolerance by orders of

@@ -6,7 +6,13 @@
 // The reference does this with four operator calls per sweep (compute save_old_ranks :85-90, reduce dangling :94-103,
 // scatter edge_op+post :105-124, reduce ranks_sum :130-135) = 4 V-passes + one E-pass with TWO gathers per edge.
 //
-// B200 design: ONE kernel per sweep, no atomics on the rank vector, no host sync inside the loop.
+// B200 design: no atomics on the rank vector, no host sync inside the loop, a fixed summation order.
+//   Round 2 (one GPU, 2-rank partitions): the rows with >= 32 edges go through the COLUMN BINS of pagerank_bins.cu — their edges
+//   regrouped by column bin, a bin's slice of the contribution vector in shared memory, 16-bit columns — so a sweep is
+//   pr_bin_kernel + pr_cold_bin_kernel + pr_sweep_kernel<false> (the rows with < 32 edges, below) + pr_finish_kernel
+//   (0.743 -> 0.53 ms per sweep at RMAT-24). What follows describes the one-kernel sweep that still runs on
+//   partitions of more than 2 ranks (and with VGLB_PR_NO_BINS), and whose tail / zero-row / epilogue code both forms share.
+//   ONE kernel per sweep:
 //   * contrib[v] = r[v]*inv[v] is produced by the epilogue of the previous sweep, so the E-pass gathers one fp32 per
 //     edge (the product is the same fp32 multiply the reference does per edge, pr.hpp:112-115).
 //   * What bounds the sweep (profiles/r1_pr_gather_lab*.txt): not HBM but the SM's L1-miss request port — one 128-byte
